@@ -1,0 +1,8 @@
+"""Import alias: the product package lives in ``hetu-galvatron_b200/`` (a name Python cannot
+import directly); this shim points ``hetu_galvatron_b200`` at that directory."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "hetu-galvatron_b200")
+__path__ = [_real]
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
