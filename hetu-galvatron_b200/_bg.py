@@ -1,0 +1,343 @@
+"""ctypes binding of the C-ABI library (include/bg_galvatron.h) + the per-rank communicator object.
+
+There is no CPU path: if ``libbg_galvatron.so`` is missing or fails to load, every use raises.  PyTorch is
+plumbing here (device memory, streams, the bootstrap exchange of IPC handles); the collectives themselves
+are the hand-written sm_100a kernels in ``csrc/``.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libbg_galvatron.so")
+
+BF16, F32 = 0, 1
+SUM, MAX = 0, 1
+MAX_PEERS = 8
+LANE_UNSHARD, LANE_REDUCE, LANE_ACT, LANE_MISC = 0, 1, 2, 3
+
+_c = ctypes
+_vp, _sz, _i, _ll, _f = _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_longlong, _c.c_float
+
+
+class bg_a2a_desc(_c.Structure):
+    _fields_ = [("src_offs", _c.POINTER(_sz)), ("dst", _vp), ("batch", _ll), ("rows", _ll), ("row_elems", _ll),
+                ("src_bs", _ll), ("src_rs", _ll), ("src_me_off", _ll), ("dst_bs", _ll), ("dst_rs", _ll),
+                ("dst_peer_off", _ll)]
+
+
+# name -> (restype, argtypes); every symbol declared in include/bg_galvatron.h
+SIGNATURES = {
+    "bg_abi_version": (_i, []),
+    "bg_last_error": (_c.c_char_p, []),
+    "bg_set_tunable": (_i, [_c.c_char_p, _ll]),
+    "bg_get_tunable": (_ll, [_c.c_char_p]),
+    "bg_launch_count": (_c.c_ulonglong, []),
+    "bg_ctx_create": (_i, [_i, _i, _i, _sz, _c.POINTER(_vp)]),
+    "bg_ctx_destroy": (_i, [_vp]),
+    "bg_arena_info": (_i, [_vp, _c.POINTER(_vp), _c.POINTER(_sz), _c.POINTER(_sz)]),
+    "bg_arena_alloc": (_i, [_vp, _sz, _c.POINTER(_sz)]),
+    "bg_arena_export": (_i, [_vp, _vp]),
+    "bg_arena_import": (_i, [_vp, _i, _vp]),
+    "bg_arena_attach_local": (_i, [_vp, _i, _vp]),
+    "bg_ctx_error_flag": (_i, [_vp, _c.POINTER(_i)]),
+    "bg_group_create": (_i, [_vp, _c.POINTER(_i), _i, _c.POINTER(_i)]),
+    "bg_group_info": (_i, [_vp, _i, _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i)]),
+    "bg_build_groups": (_i, [_i, _i, _i, _i, _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i),
+                             _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i)]),
+    "bg_barrier": (_i, [_vp, _i, _i, _vp]),
+    "bg_all_gather_cast": (_i, [_vp, _i, _i, _vp, _i, _c.POINTER(_sz), _i, _sz, _vp]),
+    "bg_reduce_scatter_acc": (_i, [_vp, _i, _i, _c.POINTER(_sz), _i, _vp, _i, _sz, _f, _f, _i, _vp]),
+    "bg_all_reduce": (_i, [_vp, _i, _i, _c.POINTER(_sz), _vp, _sz, _i, _i, _f, _vp]),
+    "bg_all_to_all_rows": (_i, [_vp, _i, _i, _c.POINTER(bg_a2a_desc), _i, _i, _vp]),
+    "bg_p2p_send": (_i, [_vp, _i, _sz, _vp, _sz, _i, _vp]),
+    "bg_p2p_wait": (_i, [_vp, _i, _i, _vp]),
+    "bg_p2p_release": (_i, [_vp, _i, _i, _vp]),
+    "bg_cast": (_i, [_vp, _i, _vp, _i, _sz, _f, _i, _vp]),
+    "bg_rmsnorm_fwd": (_i, [_vp, _vp, _vp, _vp, _ll, _ll, _f, _vp]),
+    "bg_rmsnorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _ll, _i, _vp]),
+    "bg_swiglu_fwd": (_i, [_vp, _vp, _ll, _ll, _vp]),
+    "bg_swiglu_bwd": (_i, [_vp, _vp, _vp, _ll, _ll, _vp]),
+    "bg_qkv_rope": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _ll, _ll, _ll, _ll, _i, _vp]),
+    "bg_ce_rowmax": (_i, [_vp, _i, _vp, _ll, _ll, _vp]),
+    "bg_ce_sumexp": (_i, [_vp, _i, _vp, _vp, _vp, _ll, _ll, _ll, _vp]),
+    "bg_ce_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _ll, _ll, _ll, _vp]),
+    "bg_gemm_bf16": (_i, [_vp, _vp, _vp, _ll, _ll, _ll, _i, _i, _vp]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+class BgError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded C-ABI library; raises (never falls back) when it is not built."""
+    global _lib
+    if _lib is None:
+        with _lib_lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise BgError("CUDA extension not built: %s is missing (run `python -c 'import __graft_entry__ as g; "
+                                  "g.build()'`). There is no CPU fallback." % LIB_PATH)
+                handle = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(handle, name)  # AttributeError = ABI mismatch: fail loudly
+                    fn.restype, fn.argtypes = res, args
+                if handle.bg_abi_version() != 1:
+                    raise BgError("bg_galvatron ABI version mismatch")
+                _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise BgError("bg_galvatron error %d: %s" % (rc, lib().bg_last_error().decode()))
+
+
+def set_tunable(name, value):
+    check(lib().bg_set_tunable(name.encode(), int(value)))
+
+
+def get_tunable(name):
+    return int(lib().bg_get_tunable(name.encode()))
+
+
+def launch_count():
+    return int(lib().bg_launch_count())
+
+
+def dtype_code(dt):
+    import torch
+    if dt == torch.bfloat16:
+        return BF16
+    if dt == torch.float32:
+        return F32
+    raise BgError("unsupported dtype %s (bf16/fp32 only)" % dt)
+
+
+def _stream_ptr(stream=None):
+    import torch
+    s = torch.cuda.current_stream() if stream is None else stream
+    return _vp(s.cuda_stream)
+
+
+def _ptr(t):
+    return _vp(t.data_ptr())
+
+
+class _ArenaExport:
+    """``__cuda_array_interface__`` carrier so torch can alias arena memory without copying."""
+
+    def __init__(self, ptr, nbytes, owner):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+        self._owner = owner
+
+
+class SymBuffer:
+    """A symmetric buffer: one allocation per member of ``group`` (arena offsets differ per rank)."""
+
+    def __init__(self, comm, group, nbytes, offset, tensor_u8, key):
+        self.comm, self.group, self.nbytes, self.offset, self.u8, self.key = comm, group, nbytes, offset, tensor_u8, key
+        self.offsets = None  # ctypes size_t[group.size] once exchanged
+
+    def view(self, dtype, numel=None):
+        t = self.u8.view(dtype)
+        return t if numel is None else t[:numel]
+
+    def offs(self):
+        if self.offsets is None:
+            if self.group.size == 1:
+                self.offsets = (_sz * 1)(self.offset)
+            else:
+                raise BgError("symmetric buffer %r used before BgComm.exchange()" % (self.key,))
+        return self.offsets
+
+    def sub(self, byte_offset):
+        """ctypes offsets array for a sub-range starting ``byte_offset`` bytes into every member's buffer."""
+        base = self.offs()
+        return (_sz * len(base))(*[int(o) + int(byte_offset) for o in base])
+
+
+class BgComm:
+    """One rank's handle on the peer-memory runtime: arena, groups, collectives.
+
+    ``BgComm(rank, world, device, arena_bytes)`` then either ``connect_ipc()`` (one process per GPU; handles
+    exchanged once over the bootstrap torch.distributed group) or ``BgComm.local_world(n, ...)`` (n virtual
+    ranks inside this process -- what the single-GPU parity tests use).
+    """
+
+    def __init__(self, rank, world, device, arena_bytes):
+        import torch
+        self.rank, self.world, self.device = int(rank), int(world), int(device)
+        self._ctx = _vp()
+        torch.cuda.set_device(self.device)
+        torch.cuda.init()
+        check(lib().bg_ctx_create(self.rank, self.world, self.device, int(arena_bytes), ctypes.byref(self._ctx)))
+        base, nbytes, used = _vp(), _sz(), _sz()
+        check(lib().bg_arena_info(self._ctx, ctypes.byref(base), ctypes.byref(nbytes), ctypes.byref(used)))
+        self.arena_ptr, self.arena_bytes = base.value, nbytes.value
+        self._arena_u8 = torch.as_tensor(_ArenaExport(self.arena_ptr, self.arena_bytes, self), device="cuda:%d" % self.device)
+        self._sym = {}       # key -> SymBuffer
+        self._sym_seq = {}   # group ranks -> next sequence number
+        self._pending = []   # SymBuffers whose peer offsets are not known yet
+        self._local_peers = None
+        self._gids = {}
+
+    # ---- bootstrap ------------------------------------------------------------------------------------
+    @classmethod
+    def local_world(cls, n, device=0, arena_bytes=64 << 20):
+        comms = [cls(r, n, device, arena_bytes) for r in range(n)]
+        for a in comms:
+            for b in comms:
+                if a is not b:
+                    check(lib().bg_arena_attach_local(a._ctx, b.rank, b._ctx))
+            a._local_peers = comms
+        return comms
+
+    def connect_ipc(self, pg=None):
+        """Exchange cudaIpc handles over the bootstrap process group and map every peer's arena."""
+        import torch.distributed as dist
+        if self.world == 1:
+            return
+        handle = (ctypes.c_ubyte * 64)()
+        check(lib().bg_arena_export(self._ctx, handle))
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, bytes(handle), group=pg)
+        for peer, h in enumerate(gathered):
+            if peer != self.rank:
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                check(lib().bg_arena_import(self._ctx, peer, buf))
+
+    def close(self):
+        if self._ctx:
+            self._arena_u8 = None
+            check(lib().bg_ctx_destroy(self._ctx))
+            self._ctx = _vp()
+
+    # ---- groups ---------------------------------------------------------------------------------------
+    def group_id(self, group):
+        ranks = tuple(group.ranks)
+        gid = self._gids.get(ranks)
+        if gid is None:
+            arr = (_i * len(ranks))(*ranks)
+            out = _i()
+            check(lib().bg_group_create(self._ctx, arr, len(ranks), ctypes.byref(out)))
+            gid = self._gids[ranks] = out.value
+        return gid
+
+    # ---- symmetric memory -----------------------------------------------------------------------------
+    def alloc(self, nbytes):
+        off = _sz()
+        check(lib().bg_arena_alloc(self._ctx, int(nbytes), ctypes.byref(off)))
+        return off.value, self._arena_u8[off.value: off.value + int(nbytes)]
+
+    def sym_alloc(self, group, nbytes, tag=""):
+        """Allocate the calling rank's part of a symmetric buffer.  Members must call this in the same order
+        per group (SPMD); peer offsets become known at the next ``exchange()``."""
+        nbytes = (int(nbytes) + 255) // 256 * 256
+        ranks = tuple(group.ranks)
+        seq = self._sym_seq.get(ranks, 0)
+        self._sym_seq[ranks] = seq + 1
+        key = (ranks, seq)
+        off, t = self.alloc(nbytes)
+        buf = SymBuffer(self, group, nbytes, off, t, key)
+        self._sym[key] = buf
+        if group.size > 1:
+            self._pending.append(buf)
+        return buf
+
+    def exchange(self, pg=None):
+        """Collective over the whole job: learn the peers' offsets of every pending symmetric buffer."""
+        mine = {b.key: b.offset for b in self._pending}
+        if self._local_peers is not None:
+            tables = {c.rank: {b.key: b.offset for b in c._sym.values()} for c in self._local_peers}
+        elif self.world == 1:
+            tables = {self.rank: mine}
+        else:
+            import torch.distributed as dist
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, mine, group=pg)
+            tables = dict(enumerate(gathered))
+        for b in self._pending:
+            offs = []
+            for r in b.group.ranks:
+                if b.key not in tables[r]:
+                    raise BgError("rank %d did not allocate symmetric buffer %r (allocation order differs)" % (r, b.key))
+                offs.append(tables[r][b.key])
+            b.offsets = (_sz * len(offs))(*offs)
+        self._pending = []
+
+    # ---- collectives (async on the current or given torch stream) -------------------------------------
+    def barrier(self, group, lane=LANE_MISC, stream=None):
+        check(lib().bg_barrier(self._ctx, self.group_id(group), lane, _stream_ptr(stream)))
+
+    def all_gather_cast(self, group, src, dst, shard_elems=None, lane=LANE_UNSHARD, stream=None, dst_dtype=None,
+                        dst_byte_offset=0):
+        """dst (SymBuffer) slot my_index <- cast(src) on every member."""
+        import torch
+        n = src.numel() if shard_elems is None else int(shard_elems)
+        dd = torch.bfloat16 if dst_dtype is None else dst_dtype
+        offs = dst.offs() if dst_byte_offset == 0 else dst.sub(dst_byte_offset)
+        check(lib().bg_all_gather_cast(self._ctx, self.group_id(group), lane, _ptr(src), dtype_code(src.dtype), offs,
+                                       dtype_code(dd), n, _stream_ptr(stream)))
+
+    def reduce_scatter_acc(self, group, src, src_dtype, dst, shard_elems=None, prescale=1.0, postscale=1.0,
+                           accumulate=False, lane=LANE_REDUCE, stream=None, src_byte_offset=0):
+        """dst[shard] = [dst +] sum_members(src_member[my slice]) * prescale * postscale."""
+        n = dst.numel() if shard_elems is None else int(shard_elems)
+        offs = src.offs() if src_byte_offset == 0 else src.sub(src_byte_offset)
+        check(lib().bg_reduce_scatter_acc(self._ctx, self.group_id(group), lane, offs, dtype_code(src_dtype), _ptr(dst),
+                                          dtype_code(dst.dtype), n, float(prescale), float(postscale),
+                                          1 if accumulate else 0, _stream_ptr(stream)))
+
+    def all_reduce(self, group, src, dst, elems=None, op=SUM, scale=1.0, lane=LANE_ACT, stream=None, src_byte_offset=0):
+        n = dst.numel() if elems is None else int(elems)
+        offs = src.offs() if src_byte_offset == 0 else src.sub(src_byte_offset)
+        check(lib().bg_all_reduce(self._ctx, self.group_id(group), lane, offs, _ptr(dst), n, dtype_code(dst.dtype), op,
+                                  float(scale), _stream_ptr(stream)))
+
+    def all_to_all_rows(self, group, descs, dtype, lane=LANE_ACT, stream=None):
+        """descs: list of dicts with keys src(SymBuffer) [src_byte_offset] dst(tensor) batch rows row_elems src_bs src_rs
+        src_me_off dst_bs dst_rs dst_peer_off."""
+        arr = (bg_a2a_desc * len(descs))()
+        keep = []
+        for i, d in enumerate(descs):
+            offs = d["src"].offs() if d.get("src_byte_offset", 0) == 0 else d["src"].sub(d["src_byte_offset"])
+            keep.append(offs)
+            arr[i].src_offs = ctypes.cast(offs, _c.POINTER(_sz))
+            arr[i].dst = d["dst"].data_ptr()
+            for k in ("batch", "rows", "row_elems", "src_bs", "src_rs", "src_me_off", "dst_bs", "dst_rs", "dst_peer_off"):
+                setattr(arr[i], k, int(d[k]))
+        check(lib().bg_all_to_all_rows(self._ctx, self.group_id(group), lane, arr, len(descs), dtype_code(dtype),
+                                       _stream_ptr(stream)))
+
+    def p2p_send(self, peer_rank, dst_offset, src, flag_id, stream=None):
+        check(lib().bg_p2p_send(self._ctx, int(peer_rank), int(dst_offset), _ptr(src), src.numel() * src.element_size(),
+                                int(flag_id), _stream_ptr(stream)))
+
+    def p2p_wait(self, peer_rank, flag_id, stream=None):
+        check(lib().bg_p2p_wait(self._ctx, int(peer_rank), int(flag_id), _stream_ptr(stream)))
+
+    def p2p_release(self, peer_rank, flag_id, stream=None):
+        check(lib().bg_p2p_release(self._ctx, int(peer_rank), int(flag_id), _stream_ptr(stream)))
+
+    def error_flag(self):
+        out = _i()
+        check(lib().bg_ctx_error_flag(self._ctx, ctypes.byref(out)))
+        return out.value
+
+
+# ---- local ops (no communicator needed) ---------------------------------------------------------------------
+def cast(src, dst, scale=1.0, accumulate=False, stream=None):
+    check(lib().bg_cast(_ptr(src), dtype_code(src.dtype), _ptr(dst), dtype_code(dst.dtype), src.numel(), float(scale),
+                        1 if accumulate else 0, _stream_ptr(stream)))
+
+
+def gemm_bf16(a, b, c, m, n, k, layout, accumulate=False, stream=None):
+    """layout 0: C=A[M,K]B[N,K]^T   1: C=A[M,K]B[K,N]   2: C=A[K,M]^T B[K,N]  (row-major bf16)."""
+    check(lib().bg_gemm_bf16(_ptr(a), _ptr(b), _ptr(c), int(m), int(n), int(k), int(layout), 1 if accumulate else 0,
+                             _stream_ptr(stream)))

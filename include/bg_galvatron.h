@@ -1,0 +1,159 @@
+/*
+ * bg_galvatron.h -- C ABI of the B200-native hot path behind Hetu-Galvatron's per-layer strategy API.
+ *
+ * The reference (PKU-DAIR/Hetu-Galvatron v2.4.1) has no FFI at this seam: every per-layer collective is a
+ * torch.distributed (ProcessGroupNCCL) call made from Python.  Each entry point below names the reference
+ * call site it replaces (file:line under /root/reference unless prefixed torch/).  The host side that binds
+ * these (ctypes) is hetu-galvatron_b200/_bg.py; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes, no torch types; every call returns 0 on success or a negative
+ * BG_E* code (message via bg_last_error()); nothing throws across the ABI.  All device work is asynchronous
+ * on the cudaStream_t passed as `stream` (void*).  One bg_ctx per rank (one process per GPU; several ctx in
+ * one process = "virtual ranks" on one device, used by the single-GPU parity tests).  Thread-compatible:
+ * callable from the main and the autograd thread; per-(group,lane) ordering is the caller's stream order.
+ *
+ * Peer memory model: each rank owns ONE symmetric arena (cudaMalloc, exported with cudaIpcGetMemHandle,
+ * mapped by its peers once).  A "symmetric buffer" is an array of per-member arena offsets (group order).
+ * Cross-rank synchronisation is device-side: per-(group,lane,CTA) flags in the arena head, CAS put/wait
+ * with release/acquire at .sys scope; no host sync, no NCCL on these paths.
+ */
+#ifndef BG_GALVATRON_H
+#define BG_GALVATRON_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BG_ABI_VERSION 1
+#define BG_MAX_PEERS 8      /* one NVSwitch domain */
+#define BG_MAX_WORLD 64
+#define BG_LANES 4          /* independent barrier lanes per group (e.g. unshard / grad-reduce / compute / p2p streams) */
+#define BG_MAX_CHANNELS 128 /* max CTAs of a cross-rank kernel (one barrier channel per CTA) */
+
+typedef struct bg_ctx* bg_ctx_t;
+
+enum bg_dtype { BG_BF16 = 0, BG_F32 = 1 };
+enum bg_redop { BG_SUM = 0, BG_MAX = 1 };
+enum bg_err {
+    BG_OK = 0, BG_EINVAL = -1, BG_ECUDA = -2, BG_ENOMEM = -3, BG_ENOTMAPPED = -4, BG_EGROUP = -5, BG_ETIMEOUT = -6,
+    BG_EUNSUPPORTED = -7
+};
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+int bg_abi_version(void);
+const char* bg_last_error(void);                       /* thread-local message of the last failing call */
+int bg_set_tunable(const char* name, long long value); /* "comm_ctas", "local_ctas", "timeout_ms", "oneshot_bytes" */
+long long bg_get_tunable(const char* name);
+/* how many kernels this library has launched since load (bench.py's gpu_launches) */
+unsigned long long bg_launch_count(void);
+
+/* ---- context + symmetric arena (replaces ProcessGroupNCCL communicator state) --------------------------- */
+int bg_ctx_create(int rank, int world, int device, size_t arena_bytes, bg_ctx_t* out);
+int bg_ctx_destroy(bg_ctx_t ctx);
+int bg_arena_info(bg_ctx_t ctx, void** base, size_t* bytes, size_t* used);
+int bg_arena_alloc(bg_ctx_t ctx, size_t bytes, size_t* offset);        /* 256-B aligned bump allocation */
+int bg_arena_export(bg_ctx_t ctx, void* handle64);                      /* cudaIpcMemHandle_t, 64 bytes */
+int bg_arena_import(bg_ctx_t ctx, int peer_rank, const void* handle64); /* map a peer process's arena */
+int bg_arena_attach_local(bg_ctx_t ctx, int peer_rank, bg_ctx_t peer);  /* peer ctx in this process */
+int bg_ctx_error_flag(bg_ctx_t ctx, int* flag);                         /* device-side timeout report */
+
+/* ---- groups (galvatron/core/runtime/comm_groups.py:7-29 CommGroup / :416 gen_comm_groups) ---------------- */
+/* A group is its rank list; creation is O(1), local, and needs no collective (the reference pays one
+ * torch.distributed.new_group per group on all ranks, comm_groups.py:14).  Rank lists must be arithmetic
+ * progressions (every Galvatron group is). */
+int bg_group_create(bg_ctx_t ctx, const int* ranks, int n, int* gid);
+int bg_group_info(bg_ctx_t ctx, int gid, int* n, int* my_index, int* ranks_out /* BG_MAX_PEERS */);
+/* C mirror of gen_comm_groups for one rank: for each of the n_layers whole-model rows writes the caller's
+ * tp/sp/cp/dp/sdp rank lists as (count, ranks[BG_MAX_WORLD]) records; used by the bit-exact mapping test. */
+int bg_build_groups(int rank, int world, int pp_size, int n_layers, const int* tp, const int* sp, const int* cp,
+                    int* out_counts /* [5][n_layers] */, int* out_ranks /* [5][n_layers][BG_MAX_WORLD] */,
+                    int* pp_count, int* pp_ranks /* [BG_MAX_WORLD] */);
+
+/* ---- collectives ----------------------------------------------------------------------------------------- */
+/* device-side barrier over the group (replaces torch.distributed.barrier, pipeline.py:370,698,882) */
+int bg_barrier(bg_ctx_t ctx, int gid, int lane, void* stream);
+
+/* C1  param all-gather fused with the fp32->bf16 cast.
+ * Replaces torch/distributed/fsdp/_flat_param.py:1477 all_gather_into_tensor (+ the MixedPrecision shard cast,
+ * galvatron/core/runtime/parallel.py:116-122); also the plain activation all-gathers mappings_group.py:100,
+ * layers.py:410-412, redistribute.py:65,110 when src_dtype == dst_dtype.
+ * Push: every member casts its shard once and stores it into slot `my_index` of every member's dst. */
+int bg_all_gather_cast(bg_ctx_t ctx, int gid, int lane, const void* src, int src_dtype, const size_t* dst_offs,
+                       int dst_dtype, size_t shard_elems, void* stream);
+
+/* C2  gradient reduce-scatter fused with pre/post-divide, cast and accumulate.
+ * Replaces torch/distributed/fsdp/_runtime_utils.py:852 (prediv) :858 reduce_scatter_tensor :879 (postdiv)
+ * :917-924 (cast to param dtype, += _saved_grad_shard), reached from sp_grad_reduce.py:125-126; with
+ * dst_dtype bf16 and accumulate 0 it is the Megatron-SP reduce-scatter (mappings_group.py:120, layers.py:488-494).
+ * Pull: member i reads slice i of every member's src, sums in fp32, dst = [dst +] sum * prescale * postscale. */
+int bg_reduce_scatter_acc(bg_ctx_t ctx, int gid, int lane, const size_t* src_offs, int src_dtype, void* dst,
+                          int dst_dtype, size_t shard_elems, float prescale, float postscale, int accumulate,
+                          void* stream);
+
+/* C3/C5/C6/C13/C14/C16  all-reduce (sum|max), out of place: src is a symmetric buffer, dst any local pointer.
+ * Replaces _runtime_utils.py:940 (DDP grads), mappings_group.py:19 _reduce (row-parallel fwd, layers.py:1114;
+ * column-parallel bwd, mappings_group.py:139), cross_entropy.py:22-30,61-72,78-89, grad_reduce.py:121-124.
+ * One-shot below the "oneshot_bytes" tunable, two-shot (reduce own slice, then gather) above. */
+int bg_all_reduce(bg_ctx_t ctx, int gid, int lane, const size_t* src_offs, void* dst, size_t elems, int dtype,
+                  int redop, float scale, void* stream);
+
+/* C10  Ulysses all-to-all fused with the head/seq transpose (one pass, q/k/v in one launch).
+ * Replaces transformer.py:1928-1987 single_all_to_all (permute+contiguous, dist.all_to_all_single :1977,
+ * post_all2all :1904-1925).  Pull: for each peer q and tensor t, rows of `row_elems[t]` contiguous elements:
+ *   dst_t[b*dst_bs + r*dst_rs + q*dst_peer_off + c] = src_t(peer q)[b*src_bs + r*src_rs + me*src_me_off + c] */
+typedef struct bg_a2a_desc {
+    const size_t* src_offs; /* symmetric source (arena offsets, group order) */
+    void* dst;              /* local destination */
+    long long batch, rows, row_elems;
+    long long src_bs, src_rs, src_me_off; /* element strides in the peer's source */
+    long long dst_bs, dst_rs, dst_peer_off;
+} bg_a2a_desc;
+int bg_all_to_all_rows(bg_ctx_t ctx, int gid, int lane, const bg_a2a_desc* descs, int n_descs, int dtype,
+                       void* stream);
+
+/* C11  pipeline p2p: copy `bytes` into the peer's arena at dst_off on `stream`, then raise flag `flag_id` there;
+ * the receiver's bg_p2p_wait orders its stream after the flag (no device-wide sync) and bg_p2p_release hands
+ * the slot back (a sender's 2nd..nth use of a flag first waits for that release).
+ * Replaces pipeline.py:1095-1127 batch_isend_irecv + :1244 torch.cuda.synchronize(). */
+int bg_p2p_send(bg_ctx_t ctx, int peer_rank, size_t dst_off, const void* src, size_t bytes, int flag_id,
+                void* stream);
+int bg_p2p_wait(bg_ctx_t ctx, int peer_rank, int flag_id, void* stream);
+int bg_p2p_release(bg_ctx_t ctx, int peer_rank, int flag_id, void* stream);
+
+/* ---- local fused elementwise ops adjacent to the collectives (K5/K6/K9/a10 in SURVEY 2.3) ------------------ */
+int bg_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t elems, float scale, int accumulate,
+            void* stream);
+int bg_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, long long rows, long long cols, float eps,
+                   void* stream);
+int bg_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, float* dw_partial,
+                   long long rows, long long cols, int n_partial, void* stream);
+int bg_swiglu_fwd(const void* gate_up, void* y, long long rows, long long ffn, void* stream);
+int bg_swiglu_bwd(const void* dy, const void* gate_up, void* dgate_up, long long rows, long long ffn, void* stream);
+/* fused QKV split + RoPE + [s,b,ng,(r+2)*hn] -> q [b,s,ng*r,hn], k/v [b,s,ng,hn] relayout; backward=1 is the exact
+ * transpose (reads dq,dk,dv, writes dmixed).  Replaces the split / repeat_interleave / apply_rotary_pos_emb /
+ * rearrange(...).contiguous() chain of transformer.py:731-767,842-867 (GQA stays un-expanded: flash-attn is
+ * called with ng KV heads).  cos/sin: [s, hn/2] fp32 tables for this rank's positions. */
+int bg_qkv_rope(void* mixed, void* q, void* k, void* v, const float* cos_t, const float* sin_t, long long s, long long b,
+                long long ng, long long r, long long hn, int backward, void* stream);
+
+/* a10  vocab-parallel cross-entropy (cross_entropy.py:14-152) as three row kernels around the two small
+ * all-reduces (MAX of rowmax; SUM of (sum_exp, predicted_logit)).  bg_ce_bwd overwrites logits with dlogits. */
+int bg_ce_rowmax(const void* logits, int dtype, float* rowmax, long long rows, long long vocab_local, void* stream);
+int bg_ce_sumexp(const void* logits, int dtype, const long long* target, const float* rowmax, float* out2 /* [rows][2] */,
+                 long long rows, long long vocab_local, long long vocab_start, void* stream);
+int bg_ce_bwd(void* logits, int dtype, const long long* target, const float* rowmax, const float* sum2,
+              const float* grad_loss, long long rows, long long vocab_local, long long vocab_start, void* stream);
+
+/* ---- GEMM (K1): bf16 x bf16 -> fp32 accumulate in TMEM -> bf16, tcgen05 + TMA ------------------------------ */
+/* C[M,N] (+)= A op B.  layout: 0 = "TN" C = A[M,K] * B[N,K]^T (forward, layers.py:417);
+ * 1 = "NN" C = A[M,K] * B[K,N] (dgrad, layers.py:462); 2 = "NT" C = A[K,M]^T * B[K,N] (wgrad, layers.py:534). */
+int bg_gemm_bf16(const void* a, const void* b, void* c, long long m, long long n, long long k, int layout,
+                 int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BG_GALVATRON_H */

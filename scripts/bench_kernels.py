@@ -1,0 +1,71 @@
+"""Micro-benchmarks of the C-ABI kernels on one GPU (CUDA events, warm-up, L2-exceeding inputs).
+Usage: python scripts/bench_kernels.py [gemm] [cast] [coll]  -> JSON lines on stdout."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from hetu_galvatron_b200 import _bg as bg  # noqa: E402
+
+BF = torch.bfloat16
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def gemm():
+    shapes = [(0, 8192, 6144, 4096), (0, 8192, 4096, 4096), (0, 8192, 28672, 4096), (0, 8192, 4096, 14336),
+              (1, 8192, 4096, 6144), (1, 8192, 4096, 28672), (2, 6144, 4096, 8192), (2, 28672, 4096, 8192),
+              (2, 4096, 14336, 8192), (0, 8192, 128256, 4096), (0, 8192, 8192, 8192)]
+    for layout, m, n, k in shapes:
+        a = torch.randn((k, m) if layout == 2 else (m, k), device="cuda").to(BF)
+        b = torch.randn((n, k) if layout == 0 else (k, n), device="cuda").to(BF)
+        c = torch.empty(m, n, device="cuda", dtype=BF)
+        t_mine = timeit(lambda: bg.gemm_bf16(a, b, c, m, n, k, layout))
+        at, bt = (a.t() if layout == 2 else a), (b.t() if layout == 0 else b)
+        t_ref = timeit(lambda: torch.matmul(at, bt, out=c))
+        fl = 2.0 * m * n * k
+        print(json.dumps({"bench": "gemm", "layout": layout, "m": m, "n": n, "k": k, "ms": round(t_mine, 4),
+                          "tflops": round(fl / t_mine / 1e9, 1), "cublas_ms": round(t_ref, 4),
+                          "cublas_tflops": round(fl / t_ref / 1e9, 1)}), flush=True)
+
+
+def cast():
+    n = 1 << 30
+    src = torch.randn(n, device="cuda")
+    dst = torch.empty(n, device="cuda", dtype=BF)
+    t = timeit(lambda: bg.cast(src, dst))
+    print(json.dumps({"bench": "cast_f32_bf16", "elems": n, "ms": round(t, 4), "GBps": round(n * 6 / t / 1e6, 1)}), flush=True)
+    t = timeit(lambda: dst.copy_(src))
+    print(json.dumps({"bench": "torch_copy_cast", "elems": n, "ms": round(t, 4), "GBps": round(n * 6 / t / 1e6, 1)}), flush=True)
+    # the n=1 degenerate all-gather+cast / reduce-scatter+acc (what a 1-GPU step runs per layer)
+    from hetu_galvatron_b200.core.runtime.comm_groups import CommGroup
+    P = 218_112_000
+    comm = bg.BgComm(0, 1, 0, (P * 2 + (1 << 20)) * 2)
+    grp = CommGroup([0])
+    w, g = comm.sym_alloc(grp, P * 2), comm.sym_alloc(grp, P * 2)
+    master, mg = torch.randn(P, device="cuda"), torch.zeros(P, device="cuda")
+    t = timeit(lambda: comm.all_gather_cast(grp, master, w))
+    print(json.dumps({"bench": "all_gather_cast_n1", "elems": P, "ms": round(t, 4), "GBps": round(P * 6 / t / 1e6, 1)}), flush=True)
+    t = timeit(lambda: comm.reduce_scatter_acc(grp, g, BF, mg, accumulate=True))
+    print(json.dumps({"bench": "reduce_scatter_acc_n1", "elems": P, "ms": round(t, 4), "GBps": round(P * 10 / t / 1e6, 1)}), flush=True)
+    comm.close()
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["gemm", "cast"]
+    print(json.dumps({"device": torch.cuda.get_device_name(0)}))
+    for w in which:
+        globals()[w]()
