@@ -1,0 +1,360 @@
+"""The execution backend the layer/runtime code talks to.
+
+Product = ``CudaBackend``: every method lands in a hand-written sm_100a kernel through the C ABI (``_bg``), or --
+for attention only -- in the flash-attn library the reference itself calls (transformer.py:495).
+There is no CPU implementation in this package: ``get_backend()`` raises when the extension or a GPU is missing.
+
+Host-logic tests run the same layer/schedule code on CPU by *injecting* a backend with ``set_backend()``; that
+backend (``oracle/gloo_backend.py``) lives with the oracle, is never imported from here, and is only ever installed
+by tests/ and bench.py's reference arm.
+"""
+import os
+
+import torch
+
+from . import world as _world
+
+_BACKEND = None
+
+
+def set_backend(backend):
+    global _BACKEND
+    _BACKEND = backend
+    return backend
+
+
+def get_backend():
+    global _BACKEND
+    if _BACKEND is None:
+        _BACKEND = CudaBackend()
+    return _BACKEND
+
+
+def reset_backend():
+    global _BACKEND
+    if _BACKEND is not None and hasattr(_BACKEND, "close"):
+        _BACKEND.close()
+    _BACKEND = None
+
+
+class CudaBackend:
+    """B200 backend: symmetric-memory communicator + fused kernels."""
+
+    name = "cuda-sm100a"
+    is_cuda = True
+
+    def __init__(self, comm=None, arena_bytes=None, device=None):
+        from ... import _bg
+        if not torch.cuda.is_available():
+            raise _bg.BgError("hetu-galvatron_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.bg = _bg
+        _bg.lib()
+        self.rank, self.world = _world.get_rank(), _world.get_world_size()
+        self.device_index = _world.get_local_rank() % torch.cuda.device_count() if device is None else device
+        torch.cuda.set_device(self.device_index)
+        self.device = torch.device("cuda", self.device_index)
+        if comm is None:
+            if arena_bytes is None:
+                arena_bytes = int(os.environ.get("HGB_ARENA_BYTES", 1 << 30))
+            comm = _bg.BgComm(self.rank, self.world, self.device_index, arena_bytes)
+            if self.world > 1:
+                comm.connect_ipc()
+        self.comm = comm
+        self.unshard_stream = torch.cuda.Stream(device=self.device)
+        self.reduce_stream = torch.cuda.Stream(device=self.device)
+        self.p2p_stream = torch.cuda.Stream(device=self.device)
+        self._staging = {}  # group ranks -> SymBuffer
+        self._scratch = {}
+
+    def close(self):
+        if self.comm is not None:
+            torch.cuda.synchronize()
+            self.comm.close()
+            self.comm = None
+
+    # ---- memory -------------------------------------------------------------------------------------------
+    def sym_alloc(self, group, nbytes):
+        return self.comm.sym_alloc(group, nbytes)
+
+    def exchange(self):
+        self.comm.exchange()
+
+    def reserve_staging(self, group, nbytes):
+        """Per-group activation staging buffer (peer-visible).  Must be called (identically on all members) before
+        ``exchange()``; later requests larger than the reservation raise."""
+        if group is None or group.size == 1:
+            return None
+        key = tuple(group.ranks)
+        cur = self._staging.get(key)
+        if cur is None or cur.nbytes < nbytes:
+            if cur is not None and cur.offsets is not None:
+                raise self.bg.BgError("staging buffer for group %s is %d B, need %d B (reserve before exchange())" % (key, cur.nbytes, nbytes))
+            self._staging[key] = self.comm.sym_alloc(group, nbytes)
+        return self._staging[key]
+
+    def staging(self, group, nbytes, byte_offset=0):
+        buf = self._staging.get(tuple(group.ranks))
+        if buf is None or buf.nbytes < nbytes + byte_offset:
+            raise self.bg.BgError("no staging buffer of %d B reserved for group %s" % (nbytes + byte_offset, group.ranks))
+        return buf
+
+    def staging_tensor(self, group, shape, dtype, byte_offset=0):
+        numel = 1
+        for s in shape:
+            numel *= int(s)
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        buf = self.staging(group, nbytes, byte_offset)
+        return buf.u8[byte_offset: byte_offset + nbytes].view(dtype).view(*shape), buf
+
+    def _is_staging(self, t, buf):
+        base = buf.u8.data_ptr()
+        return base <= t.data_ptr() < base + buf.nbytes
+
+    def _stage(self, x, group, byte_offset=0):
+        """Make ``x`` peer-visible: no-op when it already lives in the group's staging buffer."""
+        buf = self.staging(group, x.numel() * x.element_size(), byte_offset)
+        if self._is_staging(x, buf):
+            return buf, x.data_ptr() - buf.u8.data_ptr()
+        dst = buf.u8[byte_offset: byte_offset + x.numel() * x.element_size()].view(x.dtype)
+        dst.copy_(x.reshape(-1))
+        return buf, byte_offset
+
+    # ---- activation collectives (compute stream, LANE_ACT) ---------------------------------------------------
+    def all_reduce(self, x, group, op="sum"):
+        if group is None or group.size == 1:
+            return x
+        x = x.contiguous()
+        buf, off = self._stage(x, group)
+        out = torch.empty_like(x)
+        self.comm.all_reduce(group, buf, out, elems=_pad_elems(x), op=self.bg.MAX if op == "max" else self.bg.SUM,
+                             src_byte_offset=off) if x.numel() % _vec(x) == 0 else self._all_reduce_padded(x, group, op, out)
+        return out
+
+    def _all_reduce_padded(self, x, group, op, out):
+        n = x.numel()
+        padded = (n + 7) // 8 * 8
+        buf = self.staging(group, padded * x.element_size())
+        tmp_in = buf.u8[: padded * x.element_size()].view(x.dtype)
+        tmp_in[:n].copy_(x.reshape(-1))
+        tmp_in[n:].zero_()
+        tmp_out = torch.empty(padded, dtype=x.dtype, device=x.device)
+        self.comm.all_reduce(group, buf, tmp_out, elems=padded, op=self.bg.MAX if op == "max" else self.bg.SUM)
+        out.copy_(tmp_out[:n].view_as(out))
+
+    def all_gather_first_dim(self, x, group):
+        """[s, ...] -> [n*s, ...] in rank order (mappings_group.py:84-102 _gather_along_first_dim)."""
+        if group is None or group.size == 1:
+            return x
+        x = x.contiguous()
+        buf, off = self._stage(x, group)
+        n = group.size
+        out = torch.empty((n * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        chunk = x.numel()
+        self._check_vec(x, chunk)
+        self.comm.all_to_all_rows(group, [dict(src=buf, src_byte_offset=off, dst=out, batch=1, rows=1, row_elems=chunk,
+                                               src_bs=0, src_rs=0, src_me_off=0, dst_bs=0, dst_rs=0, dst_peer_off=chunk)], x.dtype)
+        return out
+
+    def all_gather_into_staging(self, x, group):
+        """Push all-gather whose result stays in the group's staging buffer (operand of the next GEMM only):
+        the Megatron-SP gather of layers.py:399-413."""
+        x = x.contiguous()
+        n = group.size
+        out, buf = self.staging_tensor(group, (n * x.shape[0],) + tuple(x.shape[1:]), x.dtype)
+        self._check_vec(x, x.numel())
+        self.comm.all_gather_cast(group, x, buf, shard_elems=x.numel(), lane=self.bg.LANE_ACT, dst_dtype=x.dtype)
+        return out
+
+    def reduce_scatter_first_dim(self, x, group):
+        """[n*s, ...] -> [s, ...] sum (mappings_group.py:105-122 _reduce_scatter_along_first_dim)."""
+        if group is None or group.size == 1:
+            return x
+        x = x.contiguous()
+        n = group.size
+        assert x.shape[0] % n == 0, "First dimension of the tensor should be divisible by tensor parallel size"
+        buf, off = self._stage(x, group)
+        out = torch.empty((x.shape[0] // n,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        self._check_vec(x, out.numel())
+        self.comm.reduce_scatter_acc(group, buf, x.dtype, out, shard_elems=out.numel(), lane=self.bg.LANE_ACT, src_byte_offset=off)
+        return out
+
+    def all_gather_last_dim(self, x, group):
+        """mappings_group.py:63-81 _gather_along_last_dim: gather then concatenate along the last dimension."""
+        if group is None or group.size == 1:
+            return x
+        n = group.size
+        g = self.all_gather_first_dim(x.contiguous().unsqueeze(0), group)  # [n, ...]
+        return torch.cat([g[i] for i in range(n)], dim=-1).contiguous()
+
+    def _check_vec(self, x, numel):
+        if numel % _vec(x):
+            raise self.bg.BgError("collective chunk of %d %s elements is not a multiple of 16 bytes" % (numel, x.dtype))
+
+    def ulysses_all_to_all(self, tensors, group, to_heads):
+        """Ulysses exchange of [b, s, n, d] tensors, all in ONE launch (transformer.py:1928-1987 + :2132-2145).
+        to_heads=True : [b, s/p, n, d] -> [b, s, n/p, d]  (scatter heads, gather sequence; q/k/v before attention)
+        to_heads=False: [b, s, n/p, d] -> [b, s/p, n, d]  (inverse; context after attention)"""
+        p = group.size
+        if p == 1:
+            return list(tensors)
+        descs, outs, off = [], [], 0
+        for t in tensors:
+            t = t.contiguous()
+            b, s_in, n_in, d = t.shape
+            buf, boff = self._stage(t, group, byte_offset=off)
+            off = (boff + t.numel() * t.element_size() + 255) // 256 * 256 if boff == off else off
+            if to_heads:
+                assert n_in % p == 0, "Number of heads (%d) must be divisible by the sequence parallel size (%d)!" % (n_in, p)
+                hp = n_in // p
+                out = torch.empty(b, s_in * p, hp, d, dtype=t.dtype, device=t.device)
+                descs.append(dict(src=buf, src_byte_offset=boff, dst=out, batch=b, rows=s_in, row_elems=hp * d,
+                                  src_bs=s_in * n_in * d, src_rs=n_in * d, src_me_off=hp * d,
+                                  dst_bs=s_in * p * hp * d, dst_rs=hp * d, dst_peer_off=s_in * hp * d))
+            else:
+                assert s_in % p == 0
+                sl = s_in // p
+                out = torch.empty(b, sl, n_in * p, d, dtype=t.dtype, device=t.device)
+                descs.append(dict(src=buf, src_byte_offset=boff, dst=out, batch=b, rows=sl, row_elems=n_in * d,
+                                  src_bs=s_in * n_in * d, src_rs=n_in * d, src_me_off=sl * n_in * d,
+                                  dst_bs=sl * n_in * p * d, dst_rs=n_in * p * d, dst_peer_off=n_in * d))
+            outs.append(out)
+        self.comm.all_to_all_rows(group, descs, tensors[0].dtype)
+        return outs
+
+    # ---- math ops --------------------------------------------------------------------------------------------
+    def gemm(self, a, b, layout, out=None, accumulate=False, m=None, n=None, k=None):
+        """bf16 GEMM on tcgen05.  layout 'tn': a[M,K] b[N,K]; 'nn': a[M,K] b[K,N]; 'nt': a[K,M] b[K,N]."""
+        code = {"tn": 0, "nn": 1, "nt": 2}[layout]
+        if code == 2:
+            k_, m_ = a.shape
+        else:
+            m_, k_ = a.shape
+        n_ = b.shape[0] if code == 0 else b.shape[1]
+        if out is None:
+            out = torch.empty(m_, n_, dtype=torch.bfloat16, device=a.device)
+        if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
+            raise self.bg.BgError("the B200 GEMM path is bf16-only (mixed_precision must be bf16)")
+        assert a.is_contiguous() and b.is_contiguous() and out.is_contiguous()
+        if m_ % 8 or n_ % 8 or k_ % 8:
+            raise self.bg.BgError("GEMM dims (%d,%d,%d) must be multiples of 8" % (m_, n_, k_))
+        self.bg.gemm_bf16(a, b, out, m_, n_, k_, code, accumulate=accumulate)
+        return out
+
+    def rmsnorm_fwd(self, x, weight, eps):
+        x2 = x.reshape(-1, x.shape[-1])
+        y = torch.empty_like(x2)
+        rstd = torch.empty(x2.shape[0], dtype=torch.float32, device=x.device)
+        L = self.bg.lib()
+        self.bg.check(L.bg_rmsnorm_fwd(_p(x2), _p(weight), _p(y), _p(rstd), x2.shape[0], x2.shape[1], float(eps), _s()))
+        return y.view_as(x), rstd
+
+    def rmsnorm_bwd(self, dy, x, weight, rstd):
+        x2, dy2 = x.reshape(-1, x.shape[-1]), dy.reshape(-1, x.shape[-1])
+        dx = torch.empty_like(x2)
+        npart = min(296, max(1, x2.shape[0]))
+        dwp = torch.empty(npart, x2.shape[1], dtype=torch.float32, device=x.device)
+        L = self.bg.lib()
+        self.bg.check(L.bg_rmsnorm_bwd(_p(dy2), _p(x2), _p(weight), _p(rstd), _p(dx), _p(dwp), x2.shape[0], x2.shape[1], npart, _s()))
+        return dx.view_as(x), dwp.sum(0).to(weight.dtype)
+
+    def swiglu_fwd(self, gate_up):
+        rows, two_f = gate_up.reshape(-1, gate_up.shape[-1]).shape
+        y = torch.empty(gate_up.shape[:-1] + (two_f // 2,), dtype=gate_up.dtype, device=gate_up.device)
+        self.bg.check(self.bg.lib().bg_swiglu_fwd(_p(gate_up), _p(y), rows, two_f // 2, _s()))
+        return y
+
+    def swiglu_bwd(self, dy, gate_up):
+        rows, two_f = gate_up.reshape(-1, gate_up.shape[-1]).shape
+        dgu = torch.empty_like(gate_up)
+        self.bg.check(self.bg.lib().bg_swiglu_bwd(_p(dy), _p(gate_up), _p(dgu), rows, two_f // 2, _s()))
+        return dgu
+
+    def qkv_rope_fwd(self, mixed, cos, sin, ng, r, hn, stage_group=None):
+        """mixed [s,b,ng*(r+2)*hn] -> q [b,s,ng*r,hn], k,v [b,s,ng,hn] (rotated).  With ``stage_group`` the
+        outputs are written straight into that group's staging buffer (Ulysses source, no extra copy)."""
+        s, b = mixed.shape[0], mixed.shape[1]
+        shapes = [(b, s, ng * r, hn), (b, s, ng, hn), (b, s, ng, hn)]
+        if stage_group is not None and stage_group.size > 1:
+            outs, off = [], 0
+            for sh in shapes:
+                t, _ = self.staging_tensor(stage_group, sh, mixed.dtype, byte_offset=off)
+                outs.append(t)
+                off = (off + t.numel() * t.element_size() + 255) // 256 * 256
+            q, k, v = outs
+        else:
+            q, k, v = [torch.empty(sh, dtype=mixed.dtype, device=mixed.device) for sh in shapes]
+        self.bg.check(self.bg.lib().bg_qkv_rope(_p(mixed), _p(q), _p(k), _p(v), _p(cos), _p(sin), s, b, ng, r, hn, 0, _s()))
+        return q, k, v
+
+    def qkv_rope_bwd(self, dq, dk, dv, cos, sin, ng, r, hn):
+        b, s = dq.shape[0], dq.shape[1]
+        dmixed = torch.empty(s, b, ng * (r + 2) * hn, dtype=dq.dtype, device=dq.device)
+        self.bg.check(self.bg.lib().bg_qkv_rope(_p(dmixed), _p(dq.contiguous()), _p(dk.contiguous()), _p(dv.contiguous()),
+                                                _p(cos), _p(sin), s, b, ng, r, hn, 1, _s()))
+        return dmixed
+
+    def rope_tables(self, seq_len, head_dim, base, offset, dtype, device):
+        inv_freq = 1.0 / (base ** (torch.arange(0, head_dim, 2, dtype=torch.float32, device=device) / head_dim))
+        pos = torch.arange(seq_len, dtype=torch.float32, device=device) + offset
+        freqs = torch.outer(pos, inv_freq)
+        # the reference casts cos/sin to the activation dtype before applying them (apply_rotary_pos_emb)
+        return torch.cos(freqs).to(dtype).float().contiguous(), torch.sin(freqs).to(dtype).float().contiguous()
+
+    def attention_fwd(self, q, k, v, causal, softmax_scale):
+        """flash-attn library call, as the reference (transformer.py:495 flash_attn_varlen_func; K3 is not a
+        collective and stays a dependency).  q [b,s,n,d], k/v [b,s,ng,d] (GQA un-expanded)."""
+        from flash_attn.flash_attn_interface import _flash_attn_forward
+        out, lse, _, rng = _flash_attn_forward(q, k, v, 0.0, softmax_scale, causal=causal, window_size_left=-1,
+                                               window_size_right=-1, softcap=0.0, alibi_slopes=None, return_softmax=False)
+        return out, lse, rng
+
+    def attention_bwd(self, dout, q, k, v, out, lse, causal, softmax_scale, rng):
+        from flash_attn.flash_attn_interface import _flash_attn_backward
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        _flash_attn_backward(dout.contiguous(), q, k, v, out, lse, dq, dk, dv, 0.0, softmax_scale, causal, -1, -1, 0.0, None,
+                             False, rng_state=rng)
+        return dq, dk, dv
+
+    def ce_fwd(self, logits2d, target, vocab_start, tp_group):
+        """vocab-parallel CE forward on [rows, V/t]: returns (loss[rows] fp32, rowmax, sum2) -- cross_entropy.py:14-100."""
+        L, rows, vl = self.bg.lib(), logits2d.shape[0], logits2d.shape[1]
+        code = self.bg.dtype_code(logits2d.dtype)
+        rowmax = torch.empty(rows, dtype=torch.float32, device=logits2d.device)
+        self.bg.check(L.bg_ce_rowmax(_p(logits2d), code, _p(rowmax), rows, vl, _s()))
+        rowmax = self.all_reduce(rowmax, tp_group, op="max")
+        out2 = torch.empty(rows, 2, dtype=torch.float32, device=logits2d.device)
+        self.bg.check(L.bg_ce_sumexp(_p(logits2d), code, _p(target), _p(rowmax), _p(out2), rows, vl, int(vocab_start), _s()))
+        out2 = self.all_reduce(out2, tp_group)
+        loss = torch.log(out2[:, 0]) - out2[:, 1]
+        return loss, rowmax, out2
+
+    def ce_bwd(self, logits2d, target, rowmax, sum2, grad_loss, vocab_start):
+        """in place: logits <- dlogits (cross_entropy.py:103-152)."""
+        L, rows, vl = self.bg.lib(), logits2d.shape[0], logits2d.shape[1]
+        self.bg.check(L.bg_ce_bwd(_p(logits2d), self.bg.dtype_code(logits2d.dtype), _p(target), _p(rowmax), _p(sum2),
+                                  _p(grad_loss.contiguous()), rows, vl, int(vocab_start), _s()))
+        return logits2d
+
+    def cast(self, src, dst, scale=1.0, accumulate=False):
+        self.bg.cast(src, dst, scale=scale, accumulate=accumulate)
+
+    def launch_count(self):
+        return self.bg.launch_count()
+
+
+def _vec(x):
+    return 16 // x.element_size()
+
+
+def _pad_elems(x):
+    return x.numel()
+
+
+def _p(t):
+    import ctypes
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _s():
+    import ctypes
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
