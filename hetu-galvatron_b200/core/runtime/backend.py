@@ -119,15 +119,68 @@ class CudaBackend:
         dst.copy_(x.reshape(-1))
         return buf, byte_offset
 
+    # ---- sharded-unit collectives (side streams) ------------------------------------------------------------------
+    def unit_unshard(self, unit):
+        """C1 on the unshard stream: all-gather + fp32->bf16 cast of the unit's flat parameter."""
+        with torch.cuda.stream(self.unshard_stream):
+            if unit.dp_type == "ddp":
+                self.cast(unit.flat_param.data, unit.w_flat)
+            else:
+                self.comm.all_gather_cast(unit.group, unit.flat_param.data, unit.W, shard_elems=unit.shard_elems,
+                                          lane=self.bg.LANE_UNSHARD, dst_dtype=unit.param_dtype)
+            unit._unshard_event = torch.cuda.Event()
+            unit._unshard_event.record(self.unshard_stream)
+
+    def unit_wait_unshard(self, unit):
+        if unit._unshard_event is not None:
+            torch.cuda.current_stream().wait_event(unit._unshard_event)
+            unit._unshard_event = None
+
+    def begin_step(self):
+        """The optimizer (current stream) has rewritten the masters: the unshard stream must see that."""
+        self.unshard_stream.wait_stream(torch.cuda.current_stream())
+
+    def unit_reduce(self, unit, accumulate):
+        """C2/C3 on the reduce stream, ordered after the unit's backward on the current stream."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.reduce_stream):
+            self.reduce_stream.wait_event(ev)
+            if unit.dp_type != "ddp":
+                self.comm.reduce_scatter_acc(unit.group, unit.G, unit.reduce_dtype, unit.master_grad,
+                                             shard_elems=unit.shard_elems, prescale=1.0 / unit.prediv,
+                                             postscale=1.0 / unit.postdiv, accumulate=accumulate, lane=self.bg.LANE_REDUCE)
+            elif unit.group.size == 1:
+                self.cast(unit.g_flat, unit.master_grad, accumulate=accumulate)
+            else:  # DDP layers: all-reduce of the full flat gradient (_runtime_utils.py:932-950), then cast/accumulate
+                key = (unit.reduce_dtype, unit.padded)
+                tmp = self._scratch.get(key)
+                if tmp is None:
+                    tmp = self._scratch[key] = torch.empty(unit.padded, dtype=unit.reduce_dtype, device=self.device)
+                self.comm.all_reduce(unit.group, unit.G, tmp, elems=unit.padded, scale=1.0 / (unit.prediv * unit.postdiv),
+                                     lane=self.bg.LANE_REDUCE)
+                self.cast(tmp, unit.master_grad, accumulate=accumulate)
+
+    def finish_reductions(self):
+        torch.cuda.current_stream().wait_stream(self.reduce_stream)
+
+    def make_stage_link(self, my_rank, peer_rank, max_bytes, send_flag_base, recv_flag_base):
+        from .pipeline.pipeline import _StageLink
+        return _StageLink(self, my_rank, peer_rank, max_bytes, send_flag_base, recv_flag_base)
+
     # ---- activation collectives (compute stream, LANE_ACT) ---------------------------------------------------
     def all_reduce(self, x, group, op="sum"):
         if group is None or group.size == 1:
             return x
         x = x.contiguous()
+        if x.numel() % _vec(x):
+            out = torch.empty_like(x)
+            self._all_reduce_padded(x, group, op, out)
+            return out
         buf, off = self._stage(x, group)
         out = torch.empty_like(x)
-        self.comm.all_reduce(group, buf, out, elems=_pad_elems(x), op=self.bg.MAX if op == "max" else self.bg.SUM,
-                             src_byte_offset=off) if x.numel() % _vec(x) == 0 else self._all_reduce_padded(x, group, op, out)
+        self.comm.all_reduce(group, buf, out, elems=x.numel(), op=self.bg.MAX if op == "max" else self.bg.SUM,
+                             src_byte_offset=off)
         return out
 
     def _all_reduce_padded(self, x, group, op, out):
@@ -202,7 +255,7 @@ class CudaBackend:
             t = t.contiguous()
             b, s_in, n_in, d = t.shape
             buf, boff = self._stage(t, group, byte_offset=off)
-            off = (boff + t.numel() * t.element_size() + 255) // 256 * 256 if boff == off else off
+            off = max(off, (boff + t.numel() * t.element_size() + 255) // 256 * 256)
             if to_heads:
                 assert n_in % p == 0, "Number of heads (%d) must be divisible by the sequence parallel size (%d)!" % (n_in, p)
                 hp = n_in // p
@@ -344,10 +397,6 @@ class CudaBackend:
 
 def _vec(x):
     return 16 // x.element_size()
-
-
-def _pad_elems(x):
-    return x.numel()
 
 
 def _p(t):

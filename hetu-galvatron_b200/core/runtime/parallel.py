@@ -1,0 +1,371 @@
+"""Per-layer data-parallel wrapping: the sharded unit that owns a layer's flat parameter / gradient buffers and issues
+the SDP collectives, activation checkpointing, and the relocation wrapper.
+
+Replaces ``galvatron/core/runtime/parallel.py`` (``wrap_module_fsdp_manually`` :92-199, ``wrap_modules_data_parallel``
+:316-386, ``wrap_modules_checkpoint`` :229-240, ``Module_with_relocation`` :279-313) and the FSDP1 machinery it drives
+(``torch/distributed/fsdp/_flat_param.py`` FlatParamHandle, ``_runtime_utils.py`` _unshard / _reduce_grad, plus the three
+monkey-patches in ``pipeline/grad_reduce.py`` and ``pipeline/sp_grad_reduce.py``) with one explicit state machine per
+layer whose observable semantics are the reference's:
+
+  dp type     master (fp32)        forward params (bf16)            gradient reduction
+  ddp         full                 local cast                       all-reduce          (NO_SHARD)
+  zero2       1/d shard            all-gather+cast once per step    reduce-scatter      (SHARD_GRAD_OP)
+  zero3       1/d shard            all-gather+cast fwd and bwd*     reduce-scatter      (FULL_SHARD)
+  (* the gathered copy is kept while its buffer has not been reclaimed, so the second gather is skipped when memory
+     allows; comm volume <= the reference's.)
+
+  * gradients accumulate UNSHARDED in bf16 across microbatches and are reduced once per step, on the last microbatch
+    (default ``async_grad_reduce``; grad_reduce.py:47-64,177-198) -- but each layer's reduce-scatter is launched as soon
+    as that layer's last backward finishes, on a side stream, instead of after the whole backward;
+  * with ``--no_async_grad_reduce`` every microbatch is reduced and summed into the fp32 shard (_runtime_utils.py:917-926);
+  * pre-divide / post-divide factors and padding follow FSDP (default_hooks.py:38-42, _runtime_utils.py:852,879,896-901),
+    fused into the reduce-scatter kernel together with the bf16->fp32 cast and the ``+=``;
+  * under Megatron-SP, gradients of ``sequence_parallel``-tagged params (norm weights, row-parallel bias) are summed over
+    the TP group on the last microbatch (sp_grad_reduce.py:104-123).
+"""
+import torch
+import torch.nn as nn
+
+from .backend import get_backend
+from .redistribute import fused_split_allgather
+
+_DP_TYPES = ("ddp", "zero2", "zero3")
+
+
+def fsdp_divide_factors(world_size):
+    """(predivide, postdivide) of FSDP's DefaultState (default_hooks.py:38-42): d=2->(2,1), 4->(2,2), 8->(4,2)."""
+    factor = 1
+    while world_size % factor == 0 and world_size / factor > factor:
+        factor *= 2
+    return float(factor), world_size / float(factor)
+
+
+class ShardedUnit:
+    """One layer's flat parameter, sharded over ``group`` (what an FSDP unit is in the reference)."""
+
+    def __init__(self, module, group, dp_type, name="", tp_group=None, param_dtype=torch.bfloat16, reduce_in_fp32=False,
+                 sequence_parallel=False, init_seed=None):
+        assert dp_type in _DP_TYPES, dp_type
+        be = get_backend()
+        self.be, self.module, self.group, self.dp_type, self.name = be, module, group, dp_type, name
+        self.tp_group, self.sequence_parallel = tp_group, sequence_parallel
+        self.param_dtype = param_dtype
+        self.reduce_dtype = torch.float32 if reduce_in_fp32 else param_dtype
+        self.rank_in_group = group.rank_in_group(be.rank) if group.size > 1 else 0
+        d = group.size
+        device = be.device
+
+        # ---- materialise (meta -> device) and collect parameters ---------------------------------------------
+        self._materialize(module, device, init_seed)
+        seen, params = set(), []
+        for p in module.parameters():
+            if id(p) not in seen:
+                seen.add(id(p))
+                params.append(p)
+        self.params = params
+        self.numels = [p.numel() for p in params]
+        self.offsets = [0]
+        for n in self.numels:
+            # keep every parameter 16-byte aligned inside the flat buffers (vector loads, TMA bases)
+            self.offsets.append(self.offsets[-1] + (n + 7) // 8 * 8)
+        total = self.offsets[-1]
+        self.total = total
+        self.padded = (total + 8 * d - 1) // (8 * d) * (8 * d)
+        self.shard_elems = self.padded // d
+
+        # ---- fp32 master (what the optimizer sees) ---------------------------------------------------------------
+        full = torch.zeros(self.padded, dtype=torch.float32, device=device)
+        for p, off, n in zip(params, self.offsets, self.numels):
+            full[off:off + n].copy_(p.detach().reshape(-1).float())
+        if dp_type == "ddp":
+            master = full
+        else:
+            master = full[self.rank_in_group * self.shard_elems:(self.rank_in_group + 1) * self.shard_elems].clone()
+        self.flat_param = nn.Parameter(master, requires_grad=True)
+        self.flat_param._bg_unit = self
+        self.master_grad = torch.zeros_like(master)
+
+        # ---- peer-visible flat buffers: W (gathered params) and G (unsharded grads) --------------------------------
+        esz = torch.empty((), dtype=param_dtype).element_size()
+        gsz = torch.empty((), dtype=self.reduce_dtype).element_size()
+        self.W = be.sym_alloc(group, self.padded * esz)
+        self.G = be.sym_alloc(group, self.padded * gsz)
+        self.w_flat = self.W.view(param_dtype, self.padded)
+        self.g_flat = self.G.view(self.reduce_dtype, self.padded)
+        self.g_flat.zero_()
+        self.w_flat.copy_(full.to(param_dtype))  # valid until the first optimizer step
+        for p, off, n in zip(params, self.offsets, self.numels):
+            shape = p.shape
+            p.data = self.w_flat[off:off + n].view(shape)
+            p._bg_grad = self.g_flat[off:off + n].view(shape)
+            p._bg_unit = self
+        del full
+        self._ln_params = [p for p in params if getattr(p, "sequence_parallel", False)] if (
+            sequence_parallel and tp_group is not None and tp_group.size > 1) else []
+
+        self.prediv, self.postdiv = fsdp_divide_factors(d)
+        self._started = set()          # params whose G slice holds this step's gradient
+        self._w_valid = True
+        self._unshard_event = None
+        self._reduced_this_step = False
+        self._pending = False          # backward ran since the last reduction
+        self.n_unshard = self.n_reduce = 0
+
+    # ---- construction helpers -------------------------------------------------------------------------------------
+    @staticmethod
+    def _materialize(module, device, seed):
+        """meta-device init as the reference's ``param_init_fn`` (parallel.py:79-89): to_empty + reset_parameters."""
+        has_meta = any(p.device.type == "meta" for p in module.parameters())
+        if has_meta:
+            module.to_empty(device=device)
+            gen_state = None
+            if seed is not None:
+                gen_state = torch.get_rng_state() if device.type == "cpu" else torch.cuda.get_rng_state(device)
+                torch.manual_seed(seed)
+            for sub in module.modules():
+                if callable(getattr(sub, "reset_parameters", None)) and any(True for _ in sub.parameters(recurse=False)):
+                    sub.reset_parameters()
+            if gen_state is not None:
+                torch.set_rng_state(gen_state) if device.type == "cpu" else torch.cuda.set_rng_state(gen_state, device)
+        else:
+            module.to(device)
+
+    # ---- step protocol ------------------------------------------------------------------------------------------------
+    def begin_step(self, params_changed=True):
+        """Called once per training iteration before the first forward (the optimizer has updated the master)."""
+        if params_changed:
+            self._w_valid = False
+        self._reduced_this_step = False
+        self._started.clear()
+        self._pending = False
+
+    def unshard(self):
+        """Launch (once) the all-gather + fp32->bf16 cast of this layer's parameters on the unshard stream (C1)."""
+        if self._w_valid:
+            return
+        self.be.unit_unshard(self)
+        self._w_valid = True
+        self.n_unshard += 1
+
+    def wait_unshard(self):
+        self.be.unit_wait_unshard(self)
+
+    def grad_started(self, p):
+        return id(p) in self._started
+
+    def mark_grad(self, p):
+        self._started.add(id(p))
+        self._pending = True
+
+    def _collect_autograd_grads(self):
+        """Parameters whose gradient was produced by plain autograd (norm weights, ...) -> into the flat G buffer."""
+        for p in self.params:
+            if p.grad is not None:
+                g = p.grad
+                if self.grad_started(p):
+                    p._bg_grad.add_(g.to(p._bg_grad.dtype))
+                else:
+                    p._bg_grad.copy_(g)
+                self.mark_grad(p)
+                p.grad = None
+
+    def _sum_sequence_parallel_grads(self):
+        """C4: all-reduce the norm / SP-tagged grads over the TP group (sp_grad_reduce.py:104-123), packed in one message."""
+        if not self._ln_params:
+            return
+        flat = torch.cat([p._bg_grad.reshape(-1) for p in self._ln_params])
+        pad = (-flat.numel()) % 8
+        if pad:
+            flat = torch.cat([flat, flat.new_zeros(pad)])
+        red = self.be.all_reduce(flat, self.tp_group)
+        off = 0
+        for p in self._ln_params:
+            p._bg_grad.copy_(red[off:off + p.numel()].view_as(p._bg_grad))
+            off += p.numel()
+
+    def post_backward(self, sync_gradients):
+        """After this layer's backward for one microbatch.  With ``sync_gradients`` launch the gradient reduction (C2/C3)."""
+        self._collect_autograd_grads()
+        if not sync_gradients or not self._pending:
+            return
+        be = self.be
+        for p in self.params:               # a parameter that received no gradient this step must contribute zeros
+            if not self.grad_started(p):
+                p._bg_grad.zero_()
+        self._sum_sequence_parallel_grads()
+        self.be.unit_reduce(self, accumulate=self._reduced_this_step)
+        self.flat_param.grad = self.master_grad
+        self._reduced_this_step = True
+        self._started.clear()
+        self._pending = False
+        self.n_reduce += 1
+
+    def finish_step(self):
+        """Make the optimizer (current stream) wait for this step's reductions."""
+        self.be.finish_reductions()
+
+    # ---- introspection (tests, checkpointing) ---------------------------------------------------------------------------
+    def named_slices(self, flat):
+        """name -> view of ``flat`` (a full-length flat tensor: ``w_flat``, ``g_flat`` or a gathered master)."""
+        names = {id(p): n for n, p in self.module.named_parameters()}
+        return {names[id(p)]: flat[off:off + n].view(p.shape) for p, off, n in zip(self.params, self.offsets, self.numels)}
+
+    def local_master_slices(self, tensor=None):
+        """For an un-sharded unit (group of 1, or ddp): name -> fp32 master (or ``tensor``, e.g. ``master_grad``) views."""
+        assert self.dp_type == "ddp" or self.group.size == 1, "sharded master: gather it first"
+        return self.named_slices(self.flat_param.data if tensor is None else tensor)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# module wrappers
+# ---------------------------------------------------------------------------------------------------------------------
+class _PostBackwardHook(torch.autograd.Function):
+    """Identity on the layer INPUTS; its backward runs after every gradient of the layer has been produced."""
+
+    @staticmethod
+    def forward(ctx, wrapper, *tensors):
+        ctx.wrapper = wrapper
+        return tensors if len(tensors) > 1 else tensors[0]
+
+    @staticmethod
+    def backward(ctx, *grads):
+        ctx.wrapper._post_backward()
+        return (None,) + grads
+
+
+class _PreBackwardHook(torch.autograd.Function):
+    """Identity on the layer OUTPUTS; its backward runs before the layer's backward (zero3 re-gather point)."""
+
+    @staticmethod
+    def forward(ctx, wrapper, *tensors):
+        ctx.wrapper = wrapper
+        return tensors if len(tensors) > 1 else tensors[0]
+
+    @staticmethod
+    def backward(ctx, *grads):
+        ctx.wrapper._pre_backward()
+        return (None,) + grads
+
+
+class _CheckpointFn(torch.autograd.Function):
+    """Activation checkpointing of one wrapped layer (parallel.py:229-240 checkpoint_wrapper): keep only the inputs,
+    recompute inside backward -- under the backward unshard, so no third all-gather."""
+
+    @staticmethod
+    def forward(ctx, wrapper, kwargs, *inputs):
+        ctx.wrapper, ctx.kwargs = wrapper, kwargs
+        ctx.save_for_backward(*[t for t in inputs if torch.is_tensor(t)])
+        ctx.is_tensor = [torch.is_tensor(t) for t in inputs]
+        ctx.others = [t for t in inputs if not torch.is_tensor(t)]
+        with torch.no_grad():
+            out = wrapper.module(*inputs, **kwargs)
+        return out
+
+    @staticmethod
+    def backward(ctx, *grads):
+        wrapper = ctx.wrapper
+        wrapper._pre_backward()
+        saved, others = list(ctx.saved_tensors), list(ctx.others)
+        inputs = []
+        for is_t in ctx.is_tensor:
+            if is_t:
+                t = saved.pop(0).detach()
+                t.requires_grad_(t.is_floating_point())
+                inputs.append(t)
+            else:
+                inputs.append(others.pop(0))
+        with torch.enable_grad():
+            out = wrapper.module(*inputs, **ctx.kwargs)
+        outs = out if isinstance(out, (tuple, list)) else (out,)
+        pairs = [(o, g) for o, g in zip(outs, grads) if torch.is_tensor(o) and o.requires_grad and g is not None]
+        torch.autograd.backward([o for o, _ in pairs], [g for _, g in pairs])
+        wrapper._post_backward()
+        return (None, None) + tuple(t.grad if torch.is_tensor(t) and t.requires_grad else None for t in inputs)
+
+
+class DataParallelModule(nn.Module):
+    """A pipeline-stage layer wrapped in its ShardedUnit (+ optional checkpointing).  Plays the role of the per-layer
+    FSDP wrapper (parallel.py:163-213) and of ``checkpoint_wrapper`` (parallel.py:229-240)."""
+
+    def __init__(self, module, unit, checkpoint=False):
+        super().__init__()
+        self.module, self.unit, self.checkpoint = module, unit, checkpoint
+        self.next_unit = None           # forward prefetch target (the next layer of the stage)
+        self.sync_gradients = True      # set per microbatch by the schedule (PipelineParallel.set_last_batch)
+        self._fired = True              # did _post_backward run during the current backward_step?
+
+    def _pre_backward(self):
+        self.unit.unshard()
+        self.unit.wait_unshard()
+
+    def _post_backward(self):
+        self._fired = True
+        self.unit.post_backward(self.sync_gradients)
+
+    def arm_backward(self):
+        """Called by the schedule right before ``autograd.backward`` of one microbatch."""
+        self._fired = False
+
+    def flush_backward(self):
+        """Called by the schedule right after ``autograd.backward``: layers whose inputs carry no gradient (embedding)
+        never see their input-side hook fire."""
+        if not self._fired:
+            self._post_backward()
+
+    def forward(self, *inputs, **kwargs):
+        unit = self.unit
+        unit.unshard()
+        if self.next_unit is not None:
+            self.next_unit.unshard()    # prefetch: the next layer's all-gather overlaps this layer's compute
+        unit.wait_unshard()
+        grad_mode = torch.is_grad_enabled()
+        if self.checkpoint and grad_mode:
+            # a dummy grad-requiring input keeps the node alive when no activation input requires grad
+            return _CheckpointFn.apply(self, kwargs, *inputs)
+        if grad_mode:
+            float_in = [i for i, t in enumerate(inputs) if torch.is_tensor(t) and t.is_floating_point() and t.requires_grad]
+            if float_in:
+                hooked = _PostBackwardHook.apply(self, *[inputs[i] for i in float_in])
+                hooked = hooked if isinstance(hooked, tuple) else (hooked,)
+                inputs = list(inputs)
+                for i, h in zip(float_in, hooked):
+                    inputs[i] = h
+        out = self.module(*inputs, **kwargs)
+        if grad_mode:
+            if isinstance(out, tuple):
+                out = _PreBackwardHook.apply(self, *out)
+            else:
+                out = _PreBackwardHook.apply(self, out)
+        return out
+
+
+class Module_with_relocation(nn.Module):
+    """Redistribute the activations entering a layer whose (tp|sp, cp) differs from its predecessor's
+    (parallel.py:279-313).  Float tensors take the sequence-parallel aware path, integer tensors (tokens, labels, masks)
+    the plain batch split / gather."""
+
+    def __init__(self, module, allgather_tp_sp_group, allgather_cp_group, allgather_tp_sp_cp_group, split_tp_sp_group,
+                 split_cp_group, split_tp_sp_cp_group, fused_allgather_group, fused_split_group):
+        super().__init__()
+        self.module = module
+        self.groups = (allgather_tp_sp_group, allgather_cp_group, allgather_tp_sp_cp_group, split_tp_sp_group, split_cp_group,
+                       split_tp_sp_cp_group, fused_allgather_group, fused_split_group)
+        if hasattr(module, "get_extended_attention_mask"):
+            self.get_extended_attention_mask = module.get_extended_attention_mask
+
+    def forward(self, *inputs, **kwargs):
+        moved = tuple(fused_split_allgather(x, x.is_floating_point(), *self.groups) if torch.is_tensor(x) else x for x in inputs)
+        return self.module(*moved, **kwargs)
+
+
+def wrap_modules_relocation(module_list, allgather_tp_sp_groups, allgather_cp_groups, allgather_tp_sp_cp_groups,
+                            split_tp_sp_groups, split_cp_groups, split_tp_sp_cp_groups, fused_allgather_groups,
+                            fused_split_groups):
+    """parallel.py:435-451: wrap layer i when any of its relocation groups is set."""
+    assert len(module_list) == len(allgather_tp_sp_groups) == len(fused_split_groups)
+    for i in range(len(module_list)):
+        groups = (allgather_tp_sp_groups[i], allgather_cp_groups[i], allgather_tp_sp_cp_groups[i], split_tp_sp_groups[i],
+                  split_cp_groups[i], split_tp_sp_cp_groups[i], fused_allgather_groups[i], fused_split_groups[i])
+        if any(g is not None for g in groups):
+            module_list[i] = Module_with_relocation(module_list[i], *groups)
+    return module_list

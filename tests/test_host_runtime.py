@@ -1,0 +1,83 @@
+"""Host-logic tests of the runtime (schedules, sharded units, TP / Megatron-SP / Ulysses layers, relocation, pipeline) on
+CPU: N ranks over gloo run the product's layer/schedule code on the oracle backend and must reproduce the single-process
+oracle's loss (5e-3 rel, the reference's own criterion tests/core/test_tp.py:121) and per-parameter gradients (rel-L2 < 3e-2,
+bf16 rounding noise) on the global batch.  Strategy corpus follows tests/core/test_{fsdp,tp,pp,redistributed,hybrid}.py."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_PORT = [29600]
+
+
+def launch(world, config, timeout=600):
+    _PORT[0] += 1
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(_PORT[0] + os.getpid() % 500), HOST_TEST_CONFIG=json.dumps(config), OMP_NUM_THREADS="2")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_host_worker.py")], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=timeout)[0] for p in procs]
+    for rank, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, "rank %d failed:\n%s" % (rank, out[-4000:])
+    line = [l for l in outs[0].splitlines() if l.startswith("HOST_TEST_REPORT ")][-1]
+    return json.loads(line[len("HOST_TEST_REPORT "):])
+
+
+WORLD1 = {
+    "plain": dict(),
+    "ckpt_chunks2": dict(global_checkpoint=1, chunks=2),
+    "ddp_no_async": dict(default_dp_type="ddp", chunks=2, async_grad_reduce=False),
+    "zero3": dict(sdp=1),
+}
+
+WORLD2 = {
+    "dp2_zero2": dict(default_dp_type="zero2"),
+    "dp2_zero3_ckpt_chunks2": dict(sdp=1, global_checkpoint=1, chunks=2),
+    "dp2_ddp_chunks2": dict(default_dp_type="ddp", chunks=2),
+    "dp2_zero2_no_async_chunks2": dict(default_dp_type="zero2", chunks=2, async_grad_reduce=False),
+    "tp2": dict(global_tp_deg=2, vocab_tp=2),
+    "tp2_megatron_sp": dict(global_tp_deg=2, vocab_tp=2, sequence_parallel=True),
+    "ulysses2": dict(global_tp_deg=2, use_ulysses=True, sequence_parallel=True, vocab_tp=2),
+    "pp2_1f1b_chunks4": dict(pp_deg=2, chunks=4, pipeline_type="pipedream_flush", global_train_batch_size=8),
+    "pp2_gpipe_chunks2": dict(pp_deg=2, chunks=2, pipeline_type="gpipe"),
+    "relocate_tp1_tp2": dict(_strategy_json={"pp_deg": 1, "tp_sizes_enc": "1,2", "tp_consecutive_flags": "1,1",
+                                             "dp_types_enc": "0,1", "use_sp": "0,0", "checkpoint": "0,1", "global_bsz": 4,
+                                             "chunks": 2, "default_dp_type": "zero2", "vtp": 2, "vsp": 0}),
+}
+
+WORLD4 = {
+    "tp2_dp2_sp_zero2": dict(global_tp_deg=2, vocab_tp=2, sequence_parallel=True, default_dp_type="zero2", chunks=2),
+    "pp2_tp2_1f1b": dict(pp_deg=2, global_tp_deg=2, vocab_tp=2, chunks=2, pipeline_type="pipedream_flush"),
+    "hybrid_mixed": dict(sequence_parallel=True, _spec={"n_kv_heads": 4},
+                         _strategy_json={"pp_deg": 1, "tp_sizes_enc": "2,4", "tp_consecutive_flags": "1,1", "dp_types_enc": "1,0",
+                                         "use_sp": "1,0", "checkpoint": "0,1", "global_bsz": 8, "chunks": 2,
+                                         "default_dp_type": "zero2", "vtp": 2, "vsp": 0}),
+}
+
+
+@pytest.mark.parametrize("name", sorted(WORLD1))
+def test_world1(name):
+    rep = launch(1, dict(WORLD1[name]))
+    assert rep["max_grad_err"] < 3e-2
+
+
+@pytest.mark.parametrize("name", sorted(WORLD2))
+def test_world2(name):
+    rep = launch(2, dict(WORLD2[name]))
+    assert rep["max_grad_err"] < 3e-2
+    if name == "dp2_zero2":
+        # one all-gather and one reduction per layer per step
+        assert set(rep["n_unshard"]) <= {0, 1} and set(rep["n_reduce"]) == {1}
+    if name == "dp2_zero2_no_async_chunks2":
+        assert set(rep["n_reduce"]) == {2}     # --no_async_grad_reduce: every microbatch is reduced
+
+
+@pytest.mark.parametrize("name", sorted(WORLD4))
+def test_world4(name):
+    rep = launch(4, dict(WORLD4[name]))
+    assert rep["max_grad_err"] < 3e-2
