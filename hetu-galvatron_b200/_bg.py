@@ -8,6 +8,11 @@ import ctypes
 import os
 import threading
 
+# the runtime keeps 4 streams busy at once (compute, unshard, grad-reduce, pipeline p2p) and some of their kernels wait
+# on peers: give every stream its own hardware queue so none is falsely ordered behind a waiting kernel.  Only takes
+# effect when set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libbg_galvatron.so")
 

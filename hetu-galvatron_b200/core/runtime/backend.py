@@ -55,7 +55,14 @@ class CudaBackend:
         self.device = torch.device("cuda", self.device_index)
         if comm is None:
             if arena_bytes is None:
-                arena_bytes = int(os.environ.get("HGB_ARENA_BYTES", 1 << 30))
+                arena_bytes = int(os.environ.get("HGB_ARENA_BYTES", 0))
+                if not arena_bytes:
+                    try:
+                        from .arguments import get_args
+                        arena_bytes = int(getattr(get_args(), "arena_bytes", 0))
+                    except RuntimeError:
+                        arena_bytes = 0
+                arena_bytes = arena_bytes or (1 << 30)
             comm = _bg.BgComm(self.rank, self.world, self.device_index, arena_bytes)
             if self.world > 1:
                 comm.connect_ipc()
@@ -65,6 +72,7 @@ class CudaBackend:
         self.p2p_stream = torch.cuda.Stream(device=self.device)
         self._staging = {}  # group ranks -> SymBuffer
         self._scratch = {}
+        self.gemm_profile = None   # bench.py: list of (start_event, end_event, flops) while timing the dominant kernel
 
     def close(self):
         if self.comm is not None:
@@ -290,7 +298,14 @@ class CudaBackend:
         assert a.is_contiguous() and b.is_contiguous() and out.is_contiguous()
         if m_ % 8 or n_ % 8 or k_ % 8:
             raise self.bg.BgError("GEMM dims (%d,%d,%d) must be multiples of 8" % (m_, n_, k_))
-        self.bg.gemm_bf16(a, b, out, m_, n_, k_, code, accumulate=accumulate)
+        if self.gemm_profile is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.bg.gemm_bf16(a, b, out, m_, n_, k_, code, accumulate=accumulate)
+            e1.record()
+            self.gemm_profile.append((e0, e1, 2.0 * m_ * n_ * k_))
+        else:
+            self.bg.gemm_bf16(a, b, out, m_, n_, k_, code, accumulate=accumulate)
         return out
 
     def rmsnorm_fwd(self, x, weight, eps):

@@ -23,8 +23,41 @@ def get_llama_config(args, overwrite_args=True):
     return set_model_config(config, args, overwrite_args)
 
 
+def estimate_arena_bytes(config, args, hp_configs):
+    """Bytes of peer-visible memory this rank needs: bf16 gathered params + bf16 unsharded grads of its stage's layers,
+    plus activation staging per communicating group and the pipeline receive slots."""
+    from ..core.runtime import world as _world
+    h, f, V = config.hidden_size, config.intermediate_size, args.padded_vocab_size
+    hn = h // config.num_attention_heads
+    layer = (config.num_attention_heads + 2 * config.num_key_value_heads) * hn * h + config.num_attention_heads * hn * h \
+        + 3 * f * h + 2 * h
+    pp = hp_configs["pp_deg"]
+    esz = 4 if args.mixed_precision == "fp32" else 2
+    total = 0
+    worst_stage = 0
+    for stage in range(pp):
+        n = 0
+        for tp, rank in zip(hp_configs["tp_sizes_enc"], hp_configs["pp_ranks_enc"]):
+            if rank == stage:
+                n += layer // tp if not False else layer
+        if stage == 0:
+            n += V * h // max(1, args.vocab_tp)
+        if stage == pp - 1:
+            n += V * h // max(1, args.vocab_tp) + h
+        worst_stage = max(worst_stage, n)
+    total = worst_stage * esz * 2
+    world = _world.get_world_size()
+    min_dp = max(1, world // pp // max(max(hp_configs["tp_sizes_enc"]), args.vocab_tp) // max(hp_configs["cp_sizes_enc"]))
+    mbs = -(-args.global_train_batch_size // min_dp // max(1, args.chunks if args.chunks > 0 else 1))
+    act = int(config.max_position_embeddings * mbs * h * esz * 1.5) + (1 << 20)
+    n_groups = 0 if world == 1 else 8
+    return int(total * 1.02) + act * n_groups + 4 * act + (64 << 20)
+
+
 def llama_model_hp(config, args):
     hybrid_parallel_configs = get_hybrid_parallel_configs(model_config=config, training_args=args)
+    if not getattr(args, "arena_bytes", 0):
+        args.arena_bytes = estimate_arena_bytes(config, args, hybrid_parallel_configs)
     skeleton = LlamaSkeleton(config)
     return construct_hybrid_parallel_model(model=skeleton, model_config=config, training_args=args,
                                            hybrid_parallel_configs=hybrid_parallel_configs)

@@ -19,7 +19,7 @@ def assemble_full(model, config, world, rank, tensor_of):
         flat = tensor_of(u)
         per_unit.append({"name": u.name, "tp": list(u.tp_group.ranks) if u.tp_group is not None else [rank],
                          # (a relocation wrapper adds a "module." prefix)
-                         "slices": {k[len("module."):] if k.startswith("module.") else k: v.detach().float().clone()
+                         "slices": {k[len("module."):] if k.startswith("module.") else k: v.detach().float().cpu().clone()
                                     for k, v in u.named_slices(flat).items()}})
     gathered = [None] * world
     dist.all_gather_object(gathered, per_unit)
@@ -57,10 +57,24 @@ def assemble_full(model, config, world, rank, tensor_of):
             "norm": full("norm_%d" % (L + 1), "norm.weight", None), "lm_head": full("cls_%d" % (L + 2), "lm_head.weight", 0)}
 
 
-def gathered_master_grad(be, u):
+def gathered_master_grad(be, u, world, rank):
+    """Full flat fp32 gradient of a unit: concatenate the SDP group's shards (exchanged as CPU objects)."""
     if u.dp_type == "ddp" or u.group.size == 1:
         return u.master_grad
-    return be.all_gather_first_dim(u.master_grad, u.group)
+    return None  # filled by gather_all_master_grads
+
+
+def gather_all_master_grads(model, world, rank):
+    mine = {u.name: (list(u.group.ranks), u.master_grad.detach().float().cpu()) for u in model.model.units}
+    allr = [None] * world
+    dist.all_gather_object(allr, mine)
+    full = {}
+    for u in model.model.units:
+        if u.dp_type == "ddp" or u.group.size == 1:
+            full[u.name] = u.master_grad.detach().float().cpu()
+        else:
+            full[u.name] = torch.cat([allr[r][u.name][1] for r in u.group.ranks])
+    return full
 
 
 def main():
@@ -69,21 +83,31 @@ def main():
     strategy = over.pop("_strategy_json", None)
     tol = over.pop("_tol", 3e-2)
     spec = over.pop("_spec", None)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    torch.set_num_threads(2)
+    use_cuda = os.environ.get("HOST_TEST_BACKEND", "oracle") == "cuda"
     from oracle import llama_ref
-    from oracle.gloo_backend import OracleBackend
     from hetu_galvatron_b200 import smoke_model as sm
-    from hetu_galvatron_b200.core.runtime.backend import set_backend
+    from hetu_galvatron_b200.core.runtime.backend import get_backend, set_backend
     from hetu_galvatron_b200.core.runtime.utils import get_optimizer_and_param_scheduler
-    be = set_backend(OracleBackend())
+    if use_cuda:   # the product path on real GPUs: NCCL only bootstraps (IPC handle / offset exchange)
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", torch.cuda.current_device()))
+        os.environ.setdefault("HGB_ARENA_BYTES", str(256 << 20))
+        be = get_backend()
+        be.bg.set_tunable("timeout_ms", 30000)
+        dev = be.device
+    else:
+        from oracle.gloo_backend import OracleBackend
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        torch.set_num_threads(2)
+        be = set_backend(OracleBackend())
+        dev = torch.device("cpu")
     if strategy is not None:
         over["galvatron_config_path"] = strategy
     args = sm.tiny_args(**over)
     config, model = sm.build(args, dict(sm.TINY, **spec) if spec else None)
     opt, _ = get_optimizer_and_param_scheduler(model, args)
     w = assemble_full(model, config, world, rank, lambda u: u.w_flat)
-    w = {k: (v.clone() if torch.is_tensor(v) else [{kk: vv.clone() for kk, vv in lw.items()} for lw in v]) for k, v in w.items()}
+    w = {k: (v.cpu().clone() if torch.is_tensor(v) else [{kk: vv.cpu().clone() for kk, vv in lw.items()} for lw in v]) for k, v in w.items()}
 
     gbs, seq = args.global_train_batch_size, config.max_position_embeddings
     dp_group = model.vtp_data_group
@@ -94,7 +118,11 @@ def main():
         x = torch.randint(0, config.vocab_size, (gbs, seq + 1), generator=g)
         tokens, labels = x[:, :-1].contiguous(), x[:, 1:].contiguous()
         lo, hi = dp_idx * gbs // dp, (dp_idx + 1) * gbs // dp
-        loss = model.forward_backward([tokens[lo:hi]], it, None, loss_func=None, attention_mask=None, labels=labels[lo:hi])
+        loss = model.forward_backward([tokens[lo:hi].to(dev)], it, None, loss_func=None, attention_mask=None,
+                                      labels=labels[lo:hi].to(dev))
+        if use_cuda:
+            torch.cuda.synchronize()
+            assert be.comm.error_flag() == 0
         if it == 0:
             cfg = sm.oracle_cfg(config, args)
             leaves = [w["embed"], w["norm"], w["lm_head"]] + [t for lw in w["layers"] for t in lw.values()]
@@ -102,7 +130,8 @@ def main():
                 t.requires_grad_(True)
             _, ref_loss = llama_ref.forward_loss(w, tokens, labels, cfg, dtype=torch.bfloat16)
             ref_loss.backward()
-            got = assemble_full(model, config, world, rank, lambda u: gathered_master_grad(be, u))
+            full_grads = gather_all_master_grads(model, world, rank)
+            got = assemble_full(model, config, world, rank, lambda u: full_grads[u.name])
             rel = lambda a, b: float((a.float() - b.float()).norm() / (b.float().norm() + 1e-12))  # noqa: E731
             # Reference semantics (preserved): every rank's loss is the mean over ITS cls-layer batch, and a layer's gradient
             # is averaged over that layer's SDP group (FSDP) -- so a layer whose SDP group is larger than the loss's
@@ -123,7 +152,7 @@ def main():
                 for k in gl:
                     errs["%s%d" % (k, i)] = rel(gl[k], wl[k].grad * scale["gpt_dec_%d" % (i + 1)])
             # loss: the last pipeline stage holds it; average the data-parallel replicas
-            lt = torch.tensor([loss if loss is not None else 0.0, 1.0 if loss is not None else 0.0], dtype=torch.float64)
+            lt = torch.tensor([loss if loss is not None else 0.0, 1.0 if loss is not None else 0.0], dtype=torch.float64, device=dev)
             dist.all_reduce(lt)
             mean_loss = float(lt[0] / lt[1])
             report = {"loss": mean_loss, "ref_loss": float(ref_loss), "max_grad_err": max(errs.values()),
@@ -133,9 +162,14 @@ def main():
             assert report["max_grad_err"] < tol, (report, errs)
         opt.step()
         opt.zero_grad()
+    if use_cuda:
+        report["launches"] = be.launch_count()
     if rank == 0:
         print("HOST_TEST_REPORT " + json.dumps(report), flush=True)
     dist.barrier()
+    if use_cuda:
+        from hetu_galvatron_b200.core.runtime.backend import reset_backend
+        reset_backend()
     dist.destroy_process_group()
 
 
