@@ -245,6 +245,9 @@ def run_ours(opts):
                      "launches": len(prof), "kernel_ms_per_step": round(gemm_ms / K, 3), "share_of_step": round(gemm_ms / ms_res, 4),
                      "flops_per_launch_avg": gemm_flops / max(1, len(prof)), "peak_source": peak_src},
         "clocks": clocks, "loss": {"resident": loss_res, "e2e": loss_e2e},
+        "memory_gib": {"torch_peak_allocated": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
+                       "torch_peak_reserved": round(torch.cuda.max_memory_reserved() / 2 ** 30, 2),
+                       "arena": round(be.comm.arena_bytes / 2 ** 30, 2)},
     }
     if opts.layers:
         line["invalid"] = "debug run with --layers %d: not the BASELINE workload" % opts.layers
