@@ -43,6 +43,9 @@ def parse():
     p.add_argument("--layers", type=int, default=0, help="debug only: truncate the model (the result is then marked invalid)")
     p.add_argument("--strategy", default=None, help="strategy JSON path (default: configs/ for this N)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                   help="fused: AdamW inside the gradient reduce-scatter kernel; torch: torch.optim.AdamW(fused=True) on fp32 grads")
+    p.add_argument("--checkpoint-layers", type=int, default=-1, help="override: checkpoint the first k layers")
     return p.parse_args()
 
 
@@ -118,7 +121,10 @@ def build_model(opts, strategy, backend=None):
         if "pp_division" in strategy:
             pp = strategy["pp_deg"]
             strategy["pp_division"] = ",".join([str(n // pp)] * (pp - 1) + [str(n - n // pp * (pp - 1))])
-    args = initialize_galvatron(galvatron_config_path=strategy, mixed_precision="bf16", sequence_parallel=bool(strategy.get("sequence_parallel", 0)),
+    if getattr(opts, "checkpoint_layers", -1) >= 0:
+        n_l = len(strategy["tp_sizes_enc"].split(","))
+        strategy["checkpoint"] = ",".join(["1"] * min(opts.checkpoint_layers, n_l) + ["0"] * max(0, n_l - opts.checkpoint_layers))
+    args = initialize_galvatron(galvatron_config_path=strategy, mixed_precision="bf16", fused_optimizer=getattr(opts, "optimizer", "torch") == "fused", sequence_parallel=bool(strategy.get("sequence_parallel", 0)),
                                 use_ulysses=False, init_method_std=0.02, seed=1234, local_rank=1, lr=1e-4, adam_weight_decay=0.01,
                                 make_vocab_size_divisible_by=128, vocab_tp=strategy.get("vtp", 1), model_size=opts.model,
                                 default_dp_type=strategy.get("default_dp_type", "zero2"), chunks=strategy["chunks"],
@@ -150,6 +156,7 @@ def synthetic_batches(args, config, n_steps, dp_idx, dp_size, pin):
 
 
 def run_ours(opts):
+    os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")   # 150+ GiB of long-lived state: avoid fragmentation
     import torch
     import torch.distributed as dist
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -236,7 +243,8 @@ def run_ours(opts):
                    "strategy": {k: strategy[k] for k in ("pp_deg", "chunks", "default_dp_type", "global_bsz") if k in strategy},
                    "tp": sorted(set(strategy["tp_sizes_enc"].split(","))), "checkpointed_layers": strategy.get("checkpoint", "").count("1"),
                    "layers": config.num_hidden_layers, "l2": "inputs (16 GB of bf16 weights + activations per step) far exceed the 126 MB L2",
-                   "params_per_gpu_optimizer": "AdamW(fused) on fp32 flat shards"},
+                   "optimizer": ("AdamW fused into the gradient reduce-scatter kernel (fp32 shards)" if opts.optimizer == "fused"
+                                 else "torch.optim.AdamW(fused=True) on fp32 flat shards")},
         "e2e": {"value": round(tokens_per_step * K / (ms_e2e * 1e-3), 1), "unit": "tokens/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4 * max(1, strategy["chunks"]), "ms_per_step": round(ms_e2e / K, 3)},
         "gpu_launches": int(launches),
@@ -275,7 +283,7 @@ def cpu_reference_sample(opts, budget_s=25.0):
     torch.set_num_threads(cores)
     set_backend(OracleBackend())
     sample = argparse.Namespace(**vars(opts))
-    sample.layers, sample.seq = 1, 1024
+    sample.layers, sample.seq, sample.optimizer, sample.checkpoint_layers = 1, 1024, "torch", -1
     strategy = {"pp_deg": 1, "tp_sizes_enc": "1", "tp_consecutive_flags": "1", "dp_types_enc": "0", "use_sp": "0", "checkpoint": "0",
                 "global_bsz": 1, "chunks": 1, "default_dp_type": "zero2", "vtp": 1}
     args, config, model = build_model(sample, strategy)

@@ -54,6 +54,7 @@ SIGNATURES = {
     "bg_all_gather_cast": (_i, [_vp, _i, _i, _vp, _i, _c.POINTER(_sz), _i, _sz, _vp]),
     "bg_reduce_scatter_acc": (_i, [_vp, _i, _i, _c.POINTER(_sz), _i, _vp, _i, _sz, _f, _f, _i, _vp]),
     "bg_all_reduce": (_i, [_vp, _i, _i, _c.POINTER(_sz), _vp, _sz, _i, _i, _f, _vp]),
+    "bg_reduce_scatter_adamw": (_i, [_vp, _i, _i, _c.POINTER(_sz), _i, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _f, _f, _ll, _vp]),
     "bg_all_to_all_rows": (_i, [_vp, _i, _i, _c.POINTER(bg_a2a_desc), _i, _i, _vp]),
     "bg_p2p_send": (_i, [_vp, _i, _sz, _vp, _sz, _i, _vp]),
     "bg_p2p_wait": (_i, [_vp, _i, _i, _vp]),
@@ -68,6 +69,7 @@ SIGNATURES = {
     "bg_ce_sumexp": (_i, [_vp, _i, _vp, _vp, _vp, _ll, _ll, _ll, _vp]),
     "bg_ce_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _ll, _ll, _ll, _vp]),
     "bg_gemm_bf16": (_i, [_vp, _vp, _vp, _ll, _ll, _ll, _i, _i, _vp]),
+    "bg_gemm_reduce_scatter": (_i, [_vp, _i, _i, _vp, _vp, _ll, _ll, _ll, _i, _c.POINTER(_sz), _c.POINTER(_sz), _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -299,6 +301,13 @@ class BgComm:
                                           dtype_code(dst.dtype), n, float(prescale), float(postscale),
                                           1 if accumulate else 0, _stream_ptr(stream)))
 
+    def reduce_scatter_adamw(self, group, src, src_dtype, param, exp_avg, exp_avg_sq, shard_elems, prescale, postscale, lr, beta1,
+                             beta2, eps, weight_decay, step, lane=LANE_REDUCE, stream=None):
+        check(lib().bg_reduce_scatter_adamw(self._ctx, self.group_id(group), lane, src.offs(), dtype_code(src_dtype), _ptr(param),
+                                            _ptr(exp_avg), _ptr(exp_avg_sq), int(shard_elems), float(prescale), float(postscale),
+                                            float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+                                            _stream_ptr(stream)))
+
     def all_reduce(self, group, src, dst, elems=None, op=SUM, scale=1.0, lane=LANE_ACT, stream=None, src_byte_offset=0):
         n = dst.numel() if elems is None else int(elems)
         offs = src.offs() if src_byte_offset == 0 else src.sub(src_byte_offset)
@@ -319,6 +328,13 @@ class BgComm:
                 setattr(arr[i], k, int(d[k]))
         check(lib().bg_all_to_all_rows(self._ctx, self.group_id(group), lane, arr, len(descs), dtype_code(dtype),
                                        _stream_ptr(stream)))
+
+    def gemm_reduce_scatter(self, group, a, b, m, n, k, layout, partial, partial_byte_offset, flags_byte_offset, out, reduce_stream,
+                            lane=LANE_ACT, stream=None):
+        """C = A op B reduce-scattered along M over ``group`` in one fused operation (partial tiles -> owner's HBM)."""
+        check(lib().bg_gemm_reduce_scatter(self._ctx, self.group_id(group), lane, _ptr(a), _ptr(b), int(m), int(n), int(k), int(layout),
+                                           partial.sub(partial_byte_offset), partial.sub(flags_byte_offset), _ptr(out),
+                                           _stream_ptr(stream), _vp(reduce_stream.cuda_stream)))
 
     def p2p_send(self, peer_rank, dst_offset, src, flag_id, stream=None):
         check(lib().bg_p2p_send(self._ctx, int(peer_rank), int(dst_offset), _ptr(src), src.numel() * src.element_size(),

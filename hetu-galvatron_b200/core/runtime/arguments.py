@@ -58,6 +58,7 @@ DEFAULTS = dict(
     vocab_sp=0,
     # this runtime's own knobs
     arena_bytes=0,                       # 0 = size the symmetric arena from the model
+    fused_optimizer=False,               # AdamW inside the gradient reduce-scatter kernel
 )
 
 

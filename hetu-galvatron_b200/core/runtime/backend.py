@@ -42,6 +42,7 @@ class CudaBackend:
 
     name = "cuda-sm100a"
     is_cuda = True
+    FLAG_BYTES = 1 << 16
 
     def __init__(self, comm=None, arena_bytes=None, device=None):
         from ... import _bg
@@ -70,6 +71,8 @@ class CudaBackend:
         self.unshard_stream = torch.cuda.Stream(device=self.device)
         self.reduce_stream = torch.cuda.Stream(device=self.device)
         self.p2p_stream = torch.cuda.Stream(device=self.device)
+        self.fuse_stream = torch.cuda.Stream(device=self.device)
+        self.fuse_gemm_rs = os.environ.get("HGB_FUSE_GEMM_RS", "1") != "0"
         self._staging = {}  # group ranks -> SymBuffer
         self._scratch = {}
         self.gemm_profile = None   # bench.py: list of (start_event, end_event, flops) while timing the dominant kernel
@@ -94,15 +97,19 @@ class CudaBackend:
             return None
         key = tuple(group.ranks)
         cur = self._staging.get(key)
-        if cur is None or cur.nbytes < nbytes:
+        nbytes = (int(nbytes) + 255) // 256 * 256
+        if cur is None or cur.data_bytes < nbytes:
             if cur is not None and cur.offsets is not None:
-                raise self.bg.BgError("staging buffer for group %s is %d B, need %d B (reserve before exchange())" % (key, cur.nbytes, nbytes))
-            self._staging[key] = self.comm.sym_alloc(group, nbytes)
+                raise self.bg.BgError("staging buffer for group %s is %d B, need %d B (reserve before exchange())" % (key, cur.data_bytes, nbytes))
+            buf = self.comm.sym_alloc(group, nbytes + self.FLAG_BYTES)   # tail: per-tile arrival counters of the fused GEMM+RS
+            buf.data_bytes = nbytes
+            buf.u8[nbytes:].zero_()
+            self._staging[key] = buf
         return self._staging[key]
 
     def staging(self, group, nbytes, byte_offset=0):
         buf = self._staging.get(tuple(group.ranks))
-        if buf is None or buf.nbytes < nbytes + byte_offset:
+        if buf is None or buf.data_bytes < nbytes + byte_offset:
             raise self.bg.BgError("no staging buffer of %d B reserved for group %s" % (nbytes + byte_offset, group.ranks))
         return buf
 
@@ -116,7 +123,7 @@ class CudaBackend:
 
     def _is_staging(self, t, buf):
         base = buf.u8.data_ptr()
-        return base <= t.data_ptr() < base + buf.nbytes
+        return base <= t.data_ptr() < base + buf.data_bytes
 
     def _stage(self, x, group, byte_offset=0):
         """Make ``x`` peer-visible: no-op when it already lives in the group's staging buffer."""
@@ -168,6 +175,17 @@ class CudaBackend:
                 self.comm.all_reduce(unit.group, unit.G, tmp, elems=unit.padded, scale=1.0 / (unit.prediv * unit.postdiv),
                                      lane=self.bg.LANE_REDUCE)
                 self.cast(tmp, unit.master_grad, accumulate=accumulate)
+
+    def unit_reduce_adamw(self, unit, opt):
+        """C2 with the AdamW epilogue (reduce stream): gradients are consumed in registers, no fp32 gradient shard."""
+        lr, b1, b2, eps, wd, step = opt.hyper()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.reduce_stream):
+            self.reduce_stream.wait_event(ev)
+            self.comm.reduce_scatter_adamw(unit.group, unit.G, unit.reduce_dtype, unit.flat_param.data, unit.exp_avg, unit.exp_avg_sq,
+                                           unit.shard_elems, 1.0 / unit.prediv, 1.0 / unit.postdiv, lr, b1, b2, eps, wd, step,
+                                           lane=self.bg.LANE_REDUCE)
 
     def finish_reductions(self):
         torch.cuda.current_stream().wait_stream(self.reduce_stream)
@@ -306,6 +324,29 @@ class CudaBackend:
             self.gemm_profile.append((e0, e1, 2.0 * m_ * n_ * k_))
         else:
             self.bg.gemm_bf16(a, b, out, m_, n_, k_, code, accumulate=accumulate)
+        return out
+
+    def can_fuse_gemm_rs(self, m, n, group):
+        p = 1 if group is None else group.size
+        if not self.fuse_gemm_rs or p < 2 or m % (p * 128) or n % 8:
+            return False
+        buf = self._staging.get(tuple(group.ranks))
+        tiles = (m // p // 128) * ((n + 255) // 256)
+        return buf is not None and buf.data_bytes >= m * n * 2 and tiles * 4 <= self.FLAG_BYTES
+
+    def gemm_reduce_scatter(self, a, b, layout, group):
+        """[M, N] = A op B, reduce-scattered along M over ``group`` -> [M/p, N]: the tcgen05 GEMM's epilogue stores each
+        partial tile into the owning rank's HBM and a tile reducer sums them as they land (GEMM + C8 in one operation)."""
+        code = {"tn": 0, "nn": 1, "nt": 2}[layout]
+        if code == 2:
+            k_, m_ = a.shape
+        else:
+            m_, k_ = a.shape
+        n_ = b.shape[0] if code == 0 else b.shape[1]
+        buf = self.staging(group, m_ * n_ * 2)
+        out = torch.empty(m_ // group.size, n_, dtype=torch.bfloat16, device=a.device)
+        self.comm.gemm_reduce_scatter(group, a, b, m_, n_, k_, code, buf, 0, buf.data_bytes, out, self.fuse_stream)
+        torch.cuda.current_stream().wait_stream(self.fuse_stream)
         return out
 
     def rmsnorm_fwd(self, x, weight, eps):

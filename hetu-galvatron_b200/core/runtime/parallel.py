@@ -83,7 +83,8 @@ class ShardedUnit:
             master = full[self.rank_in_group * self.shard_elems:(self.rank_in_group + 1) * self.shard_elems].clone()
         self.flat_param = nn.Parameter(master, requires_grad=True)
         self.flat_param._bg_unit = self
-        self.master_grad = torch.zeros_like(master)
+        self._master_grad = None       # fp32 gradient shard: allocated on first use (never, with the fused optimizer)
+        self.fused_opt = None          # set by FusedShardedAdamW: the reduction's epilogue applies the update
 
         # ---- peer-visible flat buffers: W (gathered params) and G (unsharded grads) --------------------------------
         esz = torch.empty((), dtype=param_dtype).element_size()
@@ -110,6 +111,16 @@ class ShardedUnit:
         self._reduced_this_step = False
         self._pending = False          # backward ran since the last reduction
         self.n_unshard = self.n_reduce = 0
+
+    @property
+    def master_grad(self):
+        if self._master_grad is None:
+            self._master_grad = torch.zeros_like(self.flat_param.data)
+        return self._master_grad
+
+    def uses_fused_optimizer(self):
+        # the fused epilogue covers the sharded (and single-rank) reduction paths; replicated DDP layers keep the plain path
+        return self.fused_opt is not None and (self.dp_type != "ddp" or self.group.size == 1)
 
     # ---- construction helpers -------------------------------------------------------------------------------------
     @staticmethod
@@ -193,8 +204,13 @@ class ShardedUnit:
             if not self.grad_started(p):
                 p._bg_grad.zero_()
         self._sum_sequence_parallel_grads()
-        self.be.unit_reduce(self, accumulate=self._reduced_this_step)
-        self.flat_param.grad = self.master_grad
+        if self.uses_fused_optimizer():
+            if self._reduced_this_step:
+                raise RuntimeError("the fused optimizer needs one gradient reduction per step (async_grad_reduce)")
+            self.be.unit_reduce_adamw(self, self.fused_opt)
+        else:
+            self.be.unit_reduce(self, accumulate=self._reduced_this_step)
+            self.flat_param.grad = self.master_grad
         self._reduced_this_step = True
         self._started.clear()
         self._pending = False

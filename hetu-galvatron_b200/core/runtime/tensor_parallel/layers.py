@@ -68,9 +68,22 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, input, weight, sequence_parallel, allreduce_dgrad, out_staged, tp_group):
+    def forward(ctx, input, weight, sequence_parallel, allreduce_dgrad, out_staged, tp_group, reduce_scatter_out=False):
         be = get_backend()
         ctx.save_for_backward(input, weight)
+        ctx.reduce_scatter_out = reduce_scatter_out and _size(tp_group) > 1
+        if ctx.reduce_scatter_out:
+            # row-parallel forward under Megatron-SP (layers.py:1061-1109): GEMM + reduce-scatter along the sequence
+            ctx.sequence_parallel, ctx.allreduce_dgrad, ctx.tp_group = False, False, tp_group
+            x2d = input.reshape(-1, input.shape[-1])
+            n_out = weight.shape[0]
+            if getattr(be, "can_fuse_gemm_rs", None) and be.can_fuse_gemm_rs(x2d.shape[0], n_out, tp_group):
+                out = be.gemm_reduce_scatter(x2d, weight, "tn", tp_group)       # one fused operation
+            else:
+                staged, _ = be.staging_tensor(tp_group, (x2d.shape[0], n_out), input.dtype)
+                be.gemm(x2d, weight, "tn", out=staged)
+                out = be.reduce_scatter_first_dim(staged, tp_group)
+            return out.view(input.shape[0] // tp_group.size, *input.shape[1:-1], n_out)
         ctx.sequence_parallel = sequence_parallel and _size(tp_group) > 1
         ctx.allreduce_dgrad = allreduce_dgrad and _size(tp_group) > 1
         ctx.tp_group = tp_group
@@ -89,6 +102,8 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
         be = get_backend()
         input, weight = ctx.saved_tensors
         group = ctx.tp_group
+        if ctx.reduce_scatter_out:   # backward of the reduce-scatter is an all-gather along the sequence (mappings_group.py:243-258)
+            grad_output = be.all_gather_first_dim(grad_output.contiguous(), group)
         dy2d = grad_output.reshape(-1, grad_output.shape[-1])
         if not dy2d.is_contiguous():
             dy2d = dy2d.contiguous()
@@ -99,7 +114,11 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
         grad_input = None
         if ctx.needs_input_grad[0]:
             m, k = dy2d.shape[0], weight.shape[1]
-            if ctx.sequence_parallel or ctx.allreduce_dgrad:
+            if ctx.sequence_parallel and getattr(be, "can_fuse_gemm_rs", None) and be.can_fuse_gemm_rs(m, k, group):
+                # dgrad GEMM + reduce-scatter along the sequence (layers.py:462,488-494) as one fused operation
+                out = be.gemm_reduce_scatter(dy2d, weight, "nn", group)
+                grad_input = out.view(grad_output.shape[0] // group.size, *grad_output.shape[1:-1], k)
+            elif ctx.sequence_parallel or ctx.allreduce_dgrad:
                 staged, _ = be.staging_tensor(group, (m, k), dy2d.dtype)  # overwrites the gathered input: wgrad is done
                 be.gemm(dy2d, weight, "nn", out=staged)
                 full_shape = grad_output.shape[:-1] + (k,)
@@ -109,15 +128,15 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
                     grad_input = be.all_reduce(staged.view(*full_shape), group)
             else:
                 grad_input = be.gemm(dy2d, weight, "nn").view(*grad_output.shape[:-1], k)
-        return grad_input, grad_weight, None, None, None, None
+        return grad_input, grad_weight, None, None, None, None, None
 
 
 def linear_with_grad_accumulation_and_async_allreduce(input, weight, bias=None, gradient_accumulation_fusion=False,
                                                       async_grad_allreduce=False, sequence_parallel=False, tp_group=None,
-                                                      out_staged=False):
+                                                      out_staged=False, reduce_scatter_out=False):
     """Same call shape as layers.py:550-648 (``async_grad_allreduce`` here means "all-reduce dgrad over tp_group")."""
     out = LinearWithGradAccumulationAndAsyncCommunication.apply(input, weight, sequence_parallel, async_grad_allreduce,
-                                                                out_staged, tp_group)
+                                                                out_staged, tp_group, reduce_scatter_out)
     return out if bias is None else out + bias
 
 
@@ -202,12 +221,15 @@ class RowParallelLinear(_ParallelLinearBase):
     def forward(self, input_):
         if not self.input_is_parallel:
             input_ = scatter_to_tensor_model_parallel_region_group(input_, self.tp_group)
-        out_parallel = linear_with_grad_accumulation_and_async_allreduce(
-            input_, self.weight, None, async_grad_allreduce=False, sequence_parallel=False, tp_group=self.tp_group,
-            out_staged=True)
         if self.sequence_parallel:
-            out = reduce_scatter_to_sequence_parallel_region_group(out_parallel, self.tp_group)   # :1109 (C8)
+            # GEMM and the sequence reduce-scatter (:1109, C8) are one operation: partial tiles go straight to their owner
+            out = linear_with_grad_accumulation_and_async_allreduce(
+                input_, self.weight, None, async_grad_allreduce=False, sequence_parallel=False, tp_group=self.tp_group,
+                reduce_scatter_out=True)
         else:
+            out_parallel = linear_with_grad_accumulation_and_async_allreduce(
+                input_, self.weight, None, async_grad_allreduce=False, sequence_parallel=False, tp_group=self.tp_group,
+                out_staged=True)
             out = reduce_from_tensor_model_parallel_region_group(out_parallel, self.tp_group)     # :1114 (C5)
         if not self.skip_bias_add and self.bias is not None:
             out = out + self.bias

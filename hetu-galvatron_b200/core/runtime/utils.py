@@ -6,7 +6,56 @@ becomes ``torch.optim.AdamW(fused=True)`` over the fp32 flat shards the sharded 
 import torch
 
 
+class FusedShardedAdamW(torch.optim.Optimizer):
+    """AdamW whose update runs inside each layer's gradient reduce-scatter kernel: when a layer's last
+    backward of the step finishes, ONE kernel pulls the peers' gradient slices, sums them and applies the AdamW step to
+    the fp32 shard -- the fp32 gradient buffer is never materialised (30 GiB less at Llama-3-8B on one GPU) and the
+    optimizer's own pass over the state disappears.  ``step()`` only advances the step counter and fences the reduce
+    stream; hyper-parameters take effect for the NEXT forward_backward.  Same rule as torch.optim.AdamW."""
+
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01):
+        params = list(model.parameters())
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.units = list(model.model.units)
+        self.step_count = 0
+        self._fallback = None
+        plain = []
+        for u in self.units:
+            u.fused_opt = self
+            if u.uses_fused_optimizer():
+                u.exp_avg = torch.zeros_like(u.flat_param.data)
+                u.exp_avg_sq = torch.zeros_like(u.flat_param.data)
+            else:
+                plain.append(u.flat_param)
+        if plain:   # replicated DDP layers: ordinary AdamW on their fp32 gradients
+            g = self.param_groups[0]
+            self._fallback = torch.optim.AdamW(plain, lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"],
+                                               fused=all(p.is_cuda for p in plain))
+
+    def hyper(self):
+        g = self.param_groups[0]
+        return g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self.step_count + 1
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        from .backend import get_backend
+        get_backend().finish_reductions()
+        if self._fallback is not None:
+            for gsrc, gdst in zip(self.param_groups, self._fallback.param_groups):
+                gdst["lr"] = gsrc["lr"]
+            self._fallback.step()
+        self.step_count += 1
+
+    def zero_grad(self, set_to_none=True):
+        if self._fallback is not None:
+            self._fallback.zero_grad(set_to_none)
+
+
 def get_optimizer_and_param_scheduler(model, args):
+    if getattr(args, "fused_optimizer", False):
+        opt = FusedShardedAdamW(model, lr=args.lr, betas=(getattr(args, "adam_beta1", 0.9), getattr(args, "adam_beta2", 0.999)),
+                                eps=getattr(args, "adam_eps", 1e-8), weight_decay=args.adam_weight_decay)
+        return opt, torch.optim.lr_scheduler.LambdaLR(opt, lambda step: 1.0)
     params = list(model.parameters())
     fused = all(p.is_cuda for p in params)
     optimizer = torch.optim.AdamW(params, lr=args.lr, weight_decay=args.adam_weight_decay,

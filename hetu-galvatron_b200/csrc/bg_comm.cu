@@ -1,5 +1,6 @@
 // bg_comm.cu -- symmetric arena, groups, device-side barriers and the peer-memory collectives
 // (SURVEY 2.3 rows C1-C3, C5-C14, C16).  sm_100a; NVLink 5 / NVSwitch peer loads & stores, no NCCL.
+#include <math.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -48,6 +49,8 @@ struct bg_ctx {
     int* err_host = nullptr;                            // mapped pinned: device-side timeout report
     int* err_dev = nullptr;
     unsigned long long p2p_sent[BG_MAX_WORLD][64] = {};
+    cudaEvent_t fused_event = nullptr, fused_barrier_event = nullptr;
+    bool fused_event_valid = false;
     std::mutex mu;
 };
 
@@ -387,8 +390,11 @@ extern "C" int bg_barrier(bg_ctx_t c, int gid, int lane, void* stream) {
 // ------------------------------------------------------------------------------------------------
 // C1: all-gather (push) fused with cast
 // ------------------------------------------------------------------------------------------------
-constexpr int kThreads = 512;
+// 256-thread CTAs with <= 128 registers: a communication CTA fits on an SM NEXT TO a persistent GEMM CTA (256 thr x 152 regs,
+// 225 KB smem), so collectives on side streams overlap the math instead of queueing behind it.
+constexpr int kThreads = 256;
 constexpr int kUnroll = 4;
+constexpr int kPullUnroll = 2;   // 16-B vectors per thread per iteration in the pull kernels (x up to 8 peers in flight)
 
 template <typename SrcT, typename DstT>
 struct Cvt;
@@ -422,7 +428,7 @@ template <> struct Cvt<float, float> {
 };
 
 template <typename SrcT, typename DstT>
-__global__ void __launch_bounds__(kThreads) all_gather_push_kernel(PeerPtrs dst, const SrcT* __restrict__ src,
+__global__ void __launch_bounds__(kThreads, 2) all_gather_push_kernel(PeerPtrs dst, const SrcT* __restrict__ src,
                                                                    size_t shard_elems, Sig s) {
     using C = Cvt<SrcT, DstT>;
     sync_peers<false, false, true>(s);  // every member has finished consuming its dst (it reached this kernel)
@@ -496,53 +502,64 @@ __device__ __forceinline__ void rs_accumulate(const uint4& v, float* acc, float 
 }
 
 template <bool kSrcBf16, bool kDstBf16>
-__global__ void __launch_bounds__(kThreads) reduce_scatter_pull_kernel(PeerPtrs src, void* __restrict__ dst,
-                                                                        size_t shard_elems, float prescale,
-                                                                        float postscale, int accumulate, Sig s) {
+__global__ void __launch_bounds__(kThreads, 2) reduce_scatter_pull_kernel(PeerPtrs src, void* __restrict__ dst,
+                                                                           size_t shard_elems, float prescale,
+                                                                           float postscale, int accumulate, Sig s) {
     constexpr int E = kSrcBf16 ? 8 : 4;  // elements per 16-B source vector
+    constexpr int U = kPullUnroll;
     sync_peers<false, false, true>(s);  // every member's src is complete (its producer kernels finished before this one)
     const size_t nvec = shard_elems / E;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t slice_off = (size_t)s.me * shard_elems * (kSrcBf16 ? 2 : 4);
-    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-        uint4 in[BG_MAX_PEERS];
+    for (size_t v0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += stride * U) {
+        uint4 in[U][BG_MAX_PEERS];
+        // issue every peer load of this iteration before consuming any: U x (n-1) 16-B NVLink loads in flight per thread
 #pragma unroll
-        for (int p = 0; p < BG_MAX_PEERS; ++p) {
-            if (p < s.n) {
-                const char* a = src.p[p] + slice_off + v * 16;
-                in[p] = (p == s.me) ? ld16_stream(a) : ld16_peer(a);
+        for (int u = 0; u < U; ++u) {
+            const size_t v = v0 + u * stride;
+#pragma unroll
+            for (int p = 0; p < BG_MAX_PEERS; ++p) {
+                if (p < s.n && v < nvec) {
+                    const char* a = src.p[p] + slice_off + v * 16;
+                    in[u][p] = (p == s.me) ? ld16_stream(a) : ld16_peer(a);
+                }
             }
         }
-        float acc[E];
 #pragma unroll
-        for (int i = 0; i < E; ++i) acc[i] = 0.f;
-        // fixed summation order (group order 0..n-1): run-to-run deterministic.  Each rank's contribution is
-        // scaled by `prescale` before the sum, as the reference pre-divides (_runtime_utils.py:852).
+        for (int u = 0; u < U; ++u) {
+            const size_t v = v0 + u * stride;
+            if (v >= nvec) break;
+            float acc[E];
 #pragma unroll
-        for (int p = 0; p < BG_MAX_PEERS; ++p)
-            if (p < s.n) rs_accumulate<kSrcBf16>(in[p], acc, prescale);
+            for (int i = 0; i < E; ++i) acc[i] = 0.f;
+            // fixed summation order (group order 0..n-1): run-to-run deterministic.  Each rank's contribution is
+            // scaled by `prescale` before the sum, as the reference pre-divides (_runtime_utils.py:852).
 #pragma unroll
-        for (int i = 0; i < E; ++i) acc[i] *= postscale;
-        if (kDstBf16) {
-            static_assert(!kDstBf16 || kSrcBf16, "bf16 dst needs bf16 src");
-            uint4* d = reinterpret_cast<uint4*>(dst) + v;
-            if (accumulate) {
-                float old[8];
-                unpack8(*d, old);
+            for (int p = 0; p < BG_MAX_PEERS; ++p)
+                if (p < s.n) rs_accumulate<kSrcBf16>(in[u][p], acc, prescale);
 #pragma unroll
-                for (int i = 0; i < E; ++i) acc[i] += old[i];
-            }
-            st16(d, pack8(acc));
-        } else {
-            float4* d = reinterpret_cast<float4*>(dst) + v * (E / 4);
-#pragma unroll
-            for (int q = 0; q < E / 4; ++q) {
-                float4 o = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            for (int i = 0; i < E; ++i) acc[i] *= postscale;
+            if (kDstBf16) {
+                static_assert(!kDstBf16 || kSrcBf16, "bf16 dst needs bf16 src");
+                uint4* d = reinterpret_cast<uint4*>(dst) + v;
                 if (accumulate) {
-                    float4 old = d[q];
-                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                    float old[8];
+                    unpack8(*d, old);
+#pragma unroll
+                    for (int i = 0; i < E; ++i) acc[i] += old[i];
                 }
-                d[q] = o;
+                st16(d, pack8(acc));
+            } else {
+                float4* d = reinterpret_cast<float4*>(dst) + v * (E / 4);
+#pragma unroll
+                for (int q = 0; q < E / 4; ++q) {
+                    float4 o = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+                    if (accumulate) {
+                        float4 old = d[q];
+                        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                    }
+                    d[q] = o;
+                }
             }
         }
     }
@@ -563,7 +580,7 @@ extern "C" int bg_reduce_scatter_acc(bg_ctx_t c, int gid, int lane, const size_t
     if (rc) return rc;
     if (shard_elems == 0) return BG_OK;
     BG_CUDA(cudaSetDevice(c->device));
-    int grid = comm_grid(shard_elems / per, kThreads, g->n);
+    int grid = comm_grid(shard_elems / per / kPullUnroll + 1, kThreads, g->n);
     cudaStream_t st = (cudaStream_t)stream;
     if (src_dtype == BG_BF16 && dst_dtype == BG_F32)
         reduce_scatter_pull_kernel<true, false><<<grid, kThreads, 0, st>>>(src, dst, shard_elems, prescale, postscale, accumulate, s);
@@ -573,6 +590,99 @@ extern "C" int bg_reduce_scatter_acc(bg_ctx_t c, int gid, int lane, const size_t
         reduce_scatter_pull_kernel<false, false><<<grid, kThreads, 0, st>>>(src, dst, shard_elems, prescale, postscale, accumulate, s);
     else
         return fail(BG_EUNSUPPORTED, "reduce_scatter %d->%d", src_dtype, dst_dtype);
+    BG_CHECK_LAUNCH();
+    return BG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C2 + optimizer: reduce-scatter whose epilogue IS the AdamW step on the fp32 shard.  The reduced gradient
+// never touches HBM: g = sum_p(G_p[slice]) * prescale * postscale stays in registers and updates (param, exp_avg, exp_avg_sq).
+// Same update rule as torch.optim.AdamW / apex FusedAdam(adam_w_mode=True) (galvatron/core/runtime/utils.py:137-150).
+// ------------------------------------------------------------------------------------------------
+struct AdamArgs {
+    float lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2_sqrt;
+};
+
+template <bool kSrcBf16>
+__global__ void __launch_bounds__(kThreads, 2) reduce_scatter_adamw_kernel(PeerPtrs src, float* __restrict__ param,
+                                                                         float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
+                                                                         size_t shard_elems, float prescale, float postscale,
+                                                                         AdamArgs a, Sig s) {
+    constexpr int E = kSrcBf16 ? 8 : 4;
+    sync_peers<false, false, true>(s);
+    const size_t nvec = shard_elems / E;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t slice_off = (size_t)s.me * shard_elems * (kSrcBf16 ? 2 : 4);
+    const float step_size = a.lr / a.bias_corr1, decay = 1.f - a.lr * a.weight_decay;
+    constexpr int U = kPullUnroll;
+    for (size_t v0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += stride * U) {
+        uint4 in[U][BG_MAX_PEERS];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t v = v0 + u * stride;
+#pragma unroll
+            for (int p = 0; p < BG_MAX_PEERS; ++p)
+                if (p < s.n && v < nvec) {
+                    const char* ad = src.p[p] + slice_off + v * 16;
+                    in[u][p] = (p == s.me) ? ld16_stream(ad) : ld16_peer(ad);
+                }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t v = v0 + u * stride;
+            if (v >= nvec) break;
+            float g[E];
+#pragma unroll
+            for (int i = 0; i < E; ++i) g[i] = 0.f;
+#pragma unroll
+            for (int p = 0; p < BG_MAX_PEERS; ++p)
+                if (p < s.n) rs_accumulate<kSrcBf16>(in[u][p], g, prescale);
+            float4* pp = reinterpret_cast<float4*>(param) + v * (E / 4);
+            float4* pm = reinterpret_cast<float4*>(exp_avg) + v * (E / 4);
+            float4* pv = reinterpret_cast<float4*>(exp_avg_sq) + v * (E / 4);
+#pragma unroll
+            for (int q = 0; q < E / 4; ++q) {
+                float4 w = pp[q], m = pm[q], vv = pv[q];
+                float* wf = reinterpret_cast<float*>(&w); float* mf = reinterpret_cast<float*>(&m); float* vf = reinterpret_cast<float*>(&vv);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float gi = g[4 * q + i] * postscale;
+                    mf[i] = a.beta1 * mf[i] + (1.f - a.beta1) * gi;
+                    vf[i] = a.beta2 * vf[i] + (1.f - a.beta2) * gi * gi;
+                    const float denom = sqrtf(vf[i]) / a.bias_corr2_sqrt + a.eps;
+                    wf[i] = wf[i] * decay - step_size * mf[i] / denom;
+                }
+                pp[q] = w; pm[q] = m; pv[q] = vv;
+            }
+        }
+    }
+    sync_peers<true, false, false>(s);
+}
+
+extern "C" int bg_reduce_scatter_adamw(bg_ctx_t c, int gid, int lane, const size_t* src_offs, int src_dtype, float* param,
+                                       float* exp_avg, float* exp_avg_sq, size_t shard_elems, float prescale, float postscale,
+                                       float lr, float beta1, float beta2, float eps, float weight_decay, long long step,
+                                       void* stream) {
+    Sig s; const Group* g;
+    int rc = make_sig(c, gid, lane, &s, &g);
+    if (rc) return rc;
+    const int per = src_dtype == BG_BF16 ? 8 : 4;
+    if (shard_elems % per) return fail(BG_EINVAL, "shard_elems %zu must be a multiple of %d", shard_elems, per);
+    if (((uintptr_t)param | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16) return fail(BG_EINVAL, "optimizer state not 16-B aligned");
+    if (step < 1) return fail(BG_EINVAL, "adam step must be >= 1");
+    PeerPtrs src;
+    rc = resolve(c, *g, src_offs, shard_elems * g->n * (src_dtype == BG_BF16 ? 2 : 4), &src);
+    if (rc) return rc;
+    if (shard_elems == 0) return BG_OK;
+    BG_CUDA(cudaSetDevice(c->device));
+    AdamArgs a;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+    a.bias_corr1 = (float)(1.0 - pow((double)beta1, (double)step));
+    a.bias_corr2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    int grid = comm_grid(shard_elems / per / kPullUnroll + 1, kThreads, g->n);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (src_dtype == BG_BF16) reduce_scatter_adamw_kernel<true><<<grid, kThreads, 0, st>>>(src, param, exp_avg, exp_avg_sq, shard_elems, prescale, postscale, a, s);
+    else reduce_scatter_adamw_kernel<false><<<grid, kThreads, 0, st>>>(src, param, exp_avg, exp_avg_sq, shard_elems, prescale, postscale, a, s);
     BG_CHECK_LAUNCH();
     return BG_OK;
 }
@@ -606,7 +716,7 @@ __device__ __forceinline__ uint4 ar_pack(const float* acc, float scale) {
 
 // one-shot: every member reads all n buffers in full
 template <bool kBf16, bool kMax>
-__global__ void __launch_bounds__(kThreads) all_reduce_oneshot_kernel(PeerPtrs src, void* __restrict__ dst, size_t nvec,
+__global__ void __launch_bounds__(kThreads, 2) all_reduce_oneshot_kernel(PeerPtrs src, void* __restrict__ dst, size_t nvec,
                                                                        float scale, Sig s) {
     constexpr int E = kBf16 ? 8 : 4;
     sync_peers<false, false, true>(s);
@@ -629,40 +739,61 @@ __global__ void __launch_bounds__(kThreads) all_reduce_oneshot_kernel(PeerPtrs s
 // Vector v of a slice is always handled by the same (CTA, thread) on every member, so the per-CTA channel
 // barrier between the two phases is sufficient.
 template <bool kBf16, bool kMax>
-__global__ void __launch_bounds__(kThreads) all_reduce_twoshot_kernel(PeerPtrs src, void* __restrict__ dst,
-                                                                       size_t slice_vec, float scale, Sig s) {
+__global__ void __launch_bounds__(kThreads, 2) all_reduce_twoshot_kernel(PeerPtrs src, void* __restrict__ dst,
+                                                                          size_t slice_vec, float scale, Sig s) {
     constexpr int E = kBf16 ? 8 : 4;
+    constexpr int U = kPullUnroll;
     sync_peers<false, false, true>(s);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t my0 = (size_t)s.me * slice_vec;
-    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < slice_vec; v += stride) {
-        uint4 in[BG_MAX_PEERS];
+    for (size_t v0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < slice_vec; v0 += stride * U) {
+        uint4 in[U][BG_MAX_PEERS];
 #pragma unroll
-        for (int p = 0; p < BG_MAX_PEERS; ++p)
-            if (p < s.n) in[p] = (p == s.me) ? ld16_stream(src.p[p] + (my0 + v) * 16) : ld16_peer(src.p[p] + (my0 + v) * 16);
-        float acc[E];
+        for (int u = 0; u < U; ++u) {
+            const size_t v = v0 + u * stride;
 #pragma unroll
-        for (int p = 0; p < BG_MAX_PEERS; ++p)
-            if (p < s.n) ar_combine<kBf16, kMax>(in[p], acc, p == 0);
-        uint4 o = ar_pack<kBf16>(acc, scale);
-        st16(src.p[s.me] + (my0 + v) * 16, o);
-        st16(reinterpret_cast<uint4*>(dst) + my0 + v, o);
+            for (int p = 0; p < BG_MAX_PEERS; ++p)
+                if (p < s.n && v < slice_vec)
+                    in[u][p] = (p == s.me) ? ld16_stream(src.p[p] + (my0 + v) * 16) : ld16_peer(src.p[p] + (my0 + v) * 16);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t v = v0 + u * stride;
+            if (v >= slice_vec) break;
+            float acc[E];
+#pragma unroll
+            for (int p = 0; p < BG_MAX_PEERS; ++p)
+                if (p < s.n) ar_combine<kBf16, kMax>(in[u][p], acc, p == 0);
+            uint4 o = ar_pack<kBf16>(acc, scale);
+            st16(src.p[s.me] + (my0 + v) * 16, o);
+            st16(reinterpret_cast<uint4*>(dst) + my0 + v, o);
+        }
     }
     sync_peers<true, true, true>(s);
-    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < slice_vec; v += stride) {
-        uint4 in[BG_MAX_PEERS];
+    // gather every member's reduced slice (vector v of a slice is handled by the same CTA on every member)
+    for (size_t v0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < slice_vec; v0 += stride * U) {
+        uint4 in[U][BG_MAX_PEERS];
 #pragma unroll
-        for (int k = 1; k < BG_MAX_PEERS; ++k)
-            if (k < s.n) {
-                int p = s.me + k; if (p >= s.n) p -= s.n;
-                in[k] = ld16_peer(src.p[p] + ((size_t)p * slice_vec + v) * 16);
-            }
+        for (int u = 0; u < U; ++u) {
+            const size_t v = v0 + u * stride;
 #pragma unroll
-        for (int k = 1; k < BG_MAX_PEERS; ++k)
-            if (k < s.n) {
-                int p = s.me + k; if (p >= s.n) p -= s.n;
-                st16(reinterpret_cast<uint4*>(dst) + (size_t)p * slice_vec + v, in[k]);
-            }
+            for (int k = 1; k < BG_MAX_PEERS; ++k)
+                if (k < s.n && v < slice_vec) {
+                    int p = s.me + k; if (p >= s.n) p -= s.n;
+                    in[u][k] = ld16_peer(src.p[p] + ((size_t)p * slice_vec + v) * 16);
+                }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t v = v0 + u * stride;
+            if (v >= slice_vec) break;
+#pragma unroll
+            for (int k = 1; k < BG_MAX_PEERS; ++k)
+                if (k < s.n) {
+                    int p = s.me + k; if (p >= s.n) p -= s.n;
+                    st16(reinterpret_cast<uint4*>(dst) + (size_t)p * slice_vec + v, in[u][k]);
+                }
+        }
     }
     sync_peers<true, false, false>(s);
 }
@@ -689,7 +820,7 @@ extern "C" int bg_all_reduce(bg_ctx_t c, int gid, int lane, const size_t* src_of
     const bool bf = dtype == BG_BF16, mx = redop == BG_MAX;
 #define BG_AR_DISPATCH(KERNEL, NV)                                                                    \
     do {                                                                                              \
-        int grid = comm_grid((NV), kThreads, g->n);                                                   \
+        int grid = comm_grid((NV) / kPullUnroll + 1, kThreads, g->n);                                                   \
         if (bf && !mx) KERNEL<true, false><<<grid, kThreads, 0, st>>>(src, dst, (NV), scale, s);      \
         else if (bf && mx) KERNEL<true, true><<<grid, kThreads, 0, st>>>(src, dst, (NV), scale, s);   \
         else if (!bf && !mx) KERNEL<false, false><<<grid, kThreads, 0, st>>>(src, dst, (NV), scale, s); \
@@ -719,7 +850,7 @@ struct A2AArgs {
     int n_tensors;
 };
 
-__global__ void __launch_bounds__(kThreads) all_to_all_rows_kernel(A2AArgs a, Sig s) {
+__global__ void __launch_bounds__(kThreads, 2) all_to_all_rows_kernel(A2AArgs a, Sig s) {
     sync_peers<false, false, true>(s);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (int ti = 0; ti < a.n_tensors; ++ti) {
@@ -853,5 +984,46 @@ extern "C" int bg_p2p_release(bg_ctx_t c, int peer, int flag_id, void* stream) {
     p2p_raise_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p2p_flag(c, peer, c->rank, flag_id, 1),
                                                         (unsigned long long)g_tun.timeout_ms * 1000000ull, c->err_dev);
     BG_CHECK_LAUNCH();
+    return BG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C5/C8 fused: GEMM whose epilogue reduce-scatters over the group (tcgen05 tiles -> peer HBM -> tile reducer)
+// ------------------------------------------------------------------------------------------------
+int bg_gemm_scatter_launch(const void* a, const void* b, long long m, long long n, long long k, int layout, int p, int me,
+                           void* const* partial_ptrs, uint32_t* const* flag_ptrs, void* out, unsigned long long timeout_ns,
+                           int* err_dev, cudaStream_t st_gemm, cudaStream_t st_reduce);
+
+extern "C" int bg_gemm_reduce_scatter(bg_ctx_t c, int gid, int lane, const void* a, const void* b, long long m, long long n,
+                                      long long k, int layout, const size_t* partial_offs, const size_t* flag_offs, void* out,
+                                      void* stream_gemm, void* stream_reduce) {
+    Sig s; const Group* g;
+    int rc = make_sig(c, gid, lane, &s, &g);
+    if (rc) return rc;
+    if (g->n < 2) return fail(BG_EINVAL, "bg_gemm_reduce_scatter needs a group of >= 2 ranks (use bg_gemm_bf16)");
+    PeerPtrs partial, flags;
+    rc = resolve(c, *g, partial_offs, (size_t)m * n * 2, &partial);
+    if (rc) return rc;
+    const size_t n_flags = (size_t)((m / g->n + 127) / 128) * ((n + 255) / 256);
+    rc = resolve(c, *g, flag_offs, n_flags * sizeof(uint32_t), &flags);
+    if (rc) return rc;
+    BG_CUDA(cudaSetDevice(c->device));
+    cudaStream_t sg = (cudaStream_t)stream_gemm, sr = (cudaStream_t)stream_reduce;
+    // the previous fused call's reducer must have drained before peers may overwrite my partial buffer: order my GEMM
+    // stream after it, then meet the peers (every member's GEMM stream passed its own previous reducer)
+    if (c->fused_event_valid) BG_CUDA(cudaStreamWaitEvent(sg, c->fused_event, 0));
+    barrier_kernel<<<1, 32, 0, sg>>>(s);
+    BG_CHECK_LAUNCH();
+    // the reducer must not look at the counters before this barrier either (they may still be mid-reset on a slow rank):
+    if (!c->fused_event_valid) { BG_CUDA(cudaEventCreateWithFlags(&c->fused_event, cudaEventDisableTiming)); BG_CUDA(cudaEventCreateWithFlags(&c->fused_barrier_event, cudaEventDisableTiming)); }
+    BG_CUDA(cudaEventRecord(c->fused_barrier_event, sg));
+    BG_CUDA(cudaStreamWaitEvent(sr, c->fused_barrier_event, 0));
+    void* pp[BG_MAX_PEERS]; uint32_t* fp[BG_MAX_PEERS];
+    for (int i = 0; i < BG_MAX_PEERS; ++i) { pp[i] = partial.p[i]; fp[i] = (uint32_t*)flags.p[i]; }
+    rc = bg_gemm_scatter_launch(a, b, m, n, k, layout, g->n, g->me, pp, fp, out, (unsigned long long)g_tun.timeout_ms * 1000000ull,
+                                c->err_dev, sg, sr);
+    if (rc) return rc;
+    BG_CUDA(cudaEventRecord(c->fused_event, sr));
+    c->fused_event_valid = true;
     return BG_OK;
 }

@@ -31,7 +31,7 @@ int fail(int code, const char* fmt, ...);
     } while (0)
 
 struct Tunables {
-    long long comm_ctas = 64;      // CTAs of a cross-rank kernel (<= BG_MAX_CHANNELS)
+    long long comm_ctas = 296;     // CTAs of a cross-rank kernel (<= BG_MAX_CHANNELS): 2 per SM, co-resident with a GEMM CTA
     long long local_ctas = 148 * 8;  // CTAs of a purely local streaming kernel
     long long timeout_ms = 60000;  // device-side barrier timeout
     long long oneshot_bytes = 512 * 1024;

@@ -129,12 +129,26 @@ __device__ __forceinline__ TileCoord tile_of(int t, int m_blocks, int n_blocks) 
     return {first_m + r % rows, r / rows};
 }
 
-template <int kLayout>
+// Fused GEMM + reduce-scatter (C5/C8): instead of storing C locally, the epilogue TMA-stores every finished 128x256 partial
+// tile straight into the HBM of the rank that owns those rows (peer store over NVLink) and bumps that rank's per-tile
+// arrival counter; a small reducer kernel on the owner sums the p partials of a tile as soon as all have landed.  Transfer and
+// math overlap tile by tile; no NCCL, no separate collective pass over the full activation.
+template <bool kScatter>
+struct ScatterParams {};
+template <>
+struct ScatterParams<true> {
+    CUtensorMap dst[BG_MAX_PEERS];      // owner o's partial buffer viewed as [p * rows_per_rank][N] (block r = source rank r)
+    uint32_t* flags[BG_MAX_PEERS];      // owner o's arrival counters, one per local tile
+    int p, me, rows_per_rank;
+};
+
+template <int kLayout, bool kScatter = false>
 __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b,
                                                                 const __grid_constant__ CUtensorMap map_c,
                                                                 const __nv_bfloat16* __restrict__ c_old, int M, int N, int K,
-                                                                int accumulate) {
+                                                                int accumulate,
+                                                                const __grid_constant__ ScatterParams<kScatter> sp) {
     constexpr bool kAMn = kLayout == kNT, kBMn = kLayout != kTN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -283,10 +297,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_con
                 fence_proxy_async();
                 epi_bar_sync();
                 if (issuer) {
-                    tma_store_2d(&map_c, smem_u32(sbuf), n0, tc.m * BLOCK_M);
+                    if constexpr (kScatter) {
+                        const int row0 = tc.m * BLOCK_M, owner = row0 / sp.rows_per_rank;
+                        tma_store_2d(&sp.dst[owner], smem_u32(sbuf), n0, sp.me * sp.rows_per_rank + (row0 - owner * sp.rows_per_rank));
+                    } else {
+                        tma_store_2d(&map_c, smem_u32(sbuf), n0, tc.m * BLOCK_M);
+                    }
                     tma_store_commit();
                 }
                 buf ^= 1;
+            }
+            if constexpr (kScatter) {
+                if (issuer) {
+                    // the whole tile has been handed to the TMA: wait until the peer stores are complete, then publish it
+                    tma_store_wait_all<0>();
+                    const int row0 = tc.m * BLOCK_M, owner = row0 / sp.rows_per_rank;
+                    const int local_tile = ((row0 - owner * sp.rows_per_rank) / BLOCK_M) * n_blocks + tc.n;
+                    __threadfence_system();
+                    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(sp.flags[owner] + local_tile) : "memory");
+                }
             }
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
@@ -329,6 +358,14 @@ int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, 
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_ERROR_INVALID_CONTEXT) {
+        // a thread (e.g. the autograd engine's) whose first CUDA call is this driver-API encode has no context bound yet:
+        // touching the runtime binds the device's primary context, then retry
+        cudaFree(0);
+        r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) return fail(BG_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld", (int)r, rows, cols);
     return BG_OK;
 }
@@ -365,9 +402,116 @@ extern "C" int bg_gemm_bf16(const void* a, const void* b, void* c, long long m, 
     const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
     cudaStream_t st = (cudaStream_t)stream;
     const __nv_bfloat16* c_old = (const __nv_bfloat16*)c;
-    if (layout == kTN) gemm_bf16_kernel<kTN><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, c_old, (int)m, (int)n, (int)k, accumulate);
-    else if (layout == kNN) gemm_bf16_kernel<kNN><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, c_old, (int)m, (int)n, (int)k, accumulate);
-    else gemm_bf16_kernel<kNT><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, c_old, (int)m, (int)n, (int)k, accumulate);
+    ScatterParams<false> none;
+    if (layout == kTN) gemm_bf16_kernel<kTN><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, c_old, (int)m, (int)n, (int)k, accumulate, none);
+    else if (layout == kNN) gemm_bf16_kernel<kNN><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, c_old, (int)m, (int)n, (int)k, accumulate, none);
+    else gemm_bf16_kernel<kNT><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, c_old, (int)m, (int)n, (int)k, accumulate, none);
+    BG_CHECK_LAUNCH();
+    return BG_OK;
+}
+
+// ---- fused GEMM + reduce-scatter -------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// One CTA per local tile (grid-strided): wait until all p partial tiles have landed, sum them in fp32, write bf16.
+__global__ void __launch_bounds__(256) tile_reduce_kernel(const __nv_bfloat16* __restrict__ partial, uint32_t* __restrict__ flags,
+                                                          __nv_bfloat16* __restrict__ out, int p, int rows_per_rank, int N,
+                                                          int n_blocks, int local_tiles, unsigned long long timeout_ns, int* err) {
+    for (int lt = blockIdx.x; lt < local_tiles; lt += gridDim.x) {
+        if (threadIdx.x == 0) {
+            unsigned long long t0 = 0;
+            unsigned spins = 0;
+            while (true) {
+                uint32_t v;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + lt) : "memory");
+                if (v >= (uint32_t)p) break;
+                if ((++spins & 0x3ff) == 0) {
+                    unsigned long long now = gtimer_ns();
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > timeout_ns) { *err = BG_ETIMEOUT; __threadfence_system(); __trap(); }
+                }
+            }
+        }
+        __syncthreads();
+        const int mb = lt / n_blocks, nb = lt % n_blocks;
+        const int row0 = mb * BLOCK_M, col0 = nb * BLOCK_N;
+        const int cols = min(BLOCK_N, N - col0), rows = min(BLOCK_M, rows_per_rank - row0);
+        const int vec_per_row = cols / 8;
+        for (int i = threadIdx.x; i < rows * vec_per_row; i += blockDim.x) {
+            const int r = i / vec_per_row, c = i - r * vec_per_row;
+            const size_t off = (size_t)(row0 + r) * N + col0 + c * 8;
+            float acc[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+            for (int src = 0; src < p; ++src) {
+                float f[8];
+                unpack8(ld16_stream(partial + (size_t)src * rows_per_rank * N + off), f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] += f[e];
+            }
+            st16(out + off, pack8(acc));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) flags[lt] = 0;   // ready for the next use (peers only write again after the next entry barrier)
+    }
+}
+
+}  // namespace
+
+// Internal entry used by bg_comm.cu (which owns contexts, groups and peer pointers).  partial/flags: per-member pointers.
+int bg_gemm_scatter_launch(const void* a, const void* b, long long m, long long n, long long k, int layout, int p, int me,
+                           void* const* partial_ptrs, uint32_t* const* flag_ptrs, void* out, unsigned long long timeout_ns,
+                           int* err_dev, cudaStream_t st_gemm, cudaStream_t st_reduce) {
+    if (layout < 0 || layout > 2) return fail(BG_EINVAL, "bg_gemm_reduce_scatter: layout %d", layout);
+    if (m <= 0 || n <= 0 || k <= 0 || n % 8 || k % 8) return fail(BG_EINVAL, "bg_gemm_reduce_scatter: bad dims");
+    if (m % ((long long)p * BLOCK_M)) return fail(BG_EINVAL, "bg_gemm_reduce_scatter: M=%lld must be a multiple of p*%d", m, BLOCK_M);
+    const int rows_per_rank = (int)(m / p);
+    CUtensorMap ma, mb;
+    int rc = layout == kNT ? make_map(&ma, a, k, m, 64, BLOCK_K) : make_map(&ma, a, m, k, BLOCK_K, BLOCK_M);
+    if (rc) return rc;
+    rc = layout == kTN ? make_map(&mb, b, n, k, BLOCK_K, BLOCK_N) : make_map(&mb, b, k, n, 64, BLOCK_K);
+    if (rc) return rc;
+    ScatterParams<true> sp;
+    sp.p = p; sp.me = me; sp.rows_per_rank = rows_per_rank;
+    for (int i = 0; i < BG_MAX_PEERS; ++i) {
+        sp.flags[i] = i < p ? flag_ptrs[i] : nullptr;
+        if (i < p) { rc = make_map(&sp.dst[i], partial_ptrs[i], (long long)p * rows_per_rank, n, kStoreCols, BLOCK_M); if (rc) return rc; }
+        else sp.dst[i] = sp.dst[0];
+    }
+    if (g_num_sms == 0) {
+        int dev = 0;
+        BG_CUDA(cudaGetDevice(&dev));
+        BG_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+        BG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kTN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        BG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        BG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    }
+    static bool scatter_attr = false;
+    if (!scatter_attr) {
+        BG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kTN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        BG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kNN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        BG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kNT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        scatter_attr = true;
+    }
+    const int m_blocks = (int)((m + BLOCK_M - 1) / BLOCK_M), n_blocks = (int)((n + BLOCK_N - 1) / BLOCK_N);
+    const long long tiles = (long long)m_blocks * n_blocks;
+    const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+    const int local_tiles = (rows_per_rank / BLOCK_M) * n_blocks;
+    // reducer first (it only waits on flags), so it is resident when the first tiles land
+    int rgrid = local_tiles < 32 ? local_tiles : 32;
+    tile_reduce_kernel<<<rgrid, 256, 0, st_reduce>>>((const __nv_bfloat16*)partial_ptrs[me], flag_ptrs[me], (__nv_bfloat16*)out, p,
+                                                     rows_per_rank, (int)n, n_blocks, local_tiles, timeout_ns, err_dev);
+    BG_CHECK_LAUNCH();
+    const CUtensorMap& mc_unused = sp.dst[0];
+    if (layout == kTN) gemm_bf16_kernel<kTN, true><<<grid, kThreads, kSmemBytes, st_gemm>>>(ma, mb, mc_unused, nullptr, (int)m, (int)n, (int)k, 0, sp);
+    else if (layout == kNN) gemm_bf16_kernel<kNN, true><<<grid, kThreads, kSmemBytes, st_gemm>>>(ma, mb, mc_unused, nullptr, (int)m, (int)n, (int)k, 0, sp);
+    else gemm_bf16_kernel<kNT, true><<<grid, kThreads, kSmemBytes, st_gemm>>>(ma, mb, mc_unused, nullptr, (int)m, (int)n, (int)k, 0, sp);
     BG_CHECK_LAUNCH();
     return BG_OK;
 }

@@ -31,7 +31,7 @@ extern "C" {
 #define BG_MAX_PEERS 8      /* one NVSwitch domain */
 #define BG_MAX_WORLD 64
 #define BG_LANES 4          /* independent barrier lanes per group (e.g. unshard / grad-reduce / compute / p2p streams) */
-#define BG_MAX_CHANNELS 128 /* max CTAs of a cross-rank kernel (one barrier channel per CTA) */
+#define BG_MAX_CHANNELS 512 /* max CTAs of a cross-rank kernel (one barrier channel per CTA) */
 
 typedef struct bg_ctx* bg_ctx_t;
 
@@ -93,6 +93,13 @@ int bg_reduce_scatter_acc(bg_ctx_t ctx, int gid, int lane, const size_t* src_off
                           int dst_dtype, size_t shard_elems, float prescale, float postscale, int accumulate,
                           void* stream);
 
+/* C2 + optimizer: the same pull reduce-scatter, but the reduced gradient is consumed in registers by an AdamW
+ * step on the caller's fp32 shard (param, exp_avg, exp_avg_sq) -- the fp32 gradient shard is never written.  Update rule of
+ * torch.optim.AdamW / apex FusedAdam adam_w_mode (galvatron/core/runtime/utils.py:137-150); `step` >= 1 for bias correction. */
+int bg_reduce_scatter_adamw(bg_ctx_t ctx, int gid, int lane, const size_t* src_offs, int src_dtype, float* param, float* exp_avg,
+                            float* exp_avg_sq, size_t shard_elems, float prescale, float postscale, float lr, float beta1,
+                            float beta2, float eps, float weight_decay, long long step, void* stream);
+
 /* C3/C5/C6/C13/C14/C16  all-reduce (sum|max), out of place: src is a symmetric buffer, dst any local pointer.
  * Replaces _runtime_utils.py:940 (DDP grads), mappings_group.py:19 _reduce (row-parallel fwd, layers.py:1114;
  * column-parallel bwd, mappings_group.py:139), cross_entropy.py:22-30,61-72,78-89, grad_reduce.py:121-124.
@@ -152,6 +159,16 @@ int bg_ce_bwd(void* logits, int dtype, const long long* target, const float* row
  * 1 = "NN" C = A[M,K] * B[K,N] (dgrad, layers.py:462); 2 = "NT" C = A[K,M]^T * B[K,N] (wgrad, layers.py:534). */
 int bg_gemm_bf16(const void* a, const void* b, void* c, long long m, long long n, long long k, int layout,
                  int accumulate, void* stream);
+
+/* C5/C8 fused with K1: C = A op B is computed in 128x256 tcgen05 tiles and REDUCE-SCATTERED along M over the group inside
+ * the same operation -- every finished partial tile is TMA-stored into the owning rank's arena (peer HBM over NVLink) and
+ * counted there; a tile reducer on the owner (stream_reduce) sums the p partials as they land and writes out[M/p, N].
+ * Replaces layers.py:1061-1109 (row-parallel GEMM then mappings_group.py:120 reduce-scatter) and :462,488-494 (dgrad +
+ * reduce-scatter).  partial_offs: symmetric bf16 buffer of M*N elements; flag_offs: symmetric u32[(M/p/128)*ceil(N/256)],
+ * zero-initialised.  M must be a multiple of p*128.  The consumer of `out` must wait for stream_reduce. */
+int bg_gemm_reduce_scatter(bg_ctx_t ctx, int gid, int lane, const void* a, const void* b, long long m, long long n, long long k,
+                           int layout, const size_t* partial_offs, const size_t* flag_offs, void* out, void* stream_gemm,
+                           void* stream_reduce);
 
 #ifdef __cplusplus
 }

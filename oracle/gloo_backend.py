@@ -126,6 +126,17 @@ class OracleBackend:
         else:
             unit.master_grad.copy_(g)
 
+    def unit_reduce_adamw(self, unit, opt):
+        """reduce (reference rounding points) then torch.optim.AdamW's update rule on the fp32 shard."""
+        self.unit_reduce(unit, accumulate=False)
+        lr, b1, b2, eps, wd, step = opt.hyper()
+        g, p = unit.master_grad, unit.flat_param.data
+        p.mul_(1 - lr * wd)
+        unit.exp_avg.mul_(b1).add_(g, alpha=1 - b1)
+        unit.exp_avg_sq.mul_(b2).addcmul_(g, g, value=1 - b2)
+        denom = (unit.exp_avg_sq.sqrt() / math.sqrt(1 - b2 ** step)).add_(eps)
+        p.addcdiv_(unit.exp_avg, denom, value=-lr / (1 - b1 ** step))
+
     def make_stage_link(self, my_rank, peer_rank, max_bytes, send_flag_base, recv_flag_base):
         return _Link(peer_rank)
 

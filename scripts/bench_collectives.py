@@ -20,17 +20,20 @@ from hetu_galvatron_b200.core.runtime.comm_groups import CommGroup  # noqa: E402
 BF = torch.bfloat16
 
 
-def timed(fn, iters=10, warm=3):
+def timed(fn, iters=20, warm=5):
+    """Per-launch CUDA events (the kernels wait for their peers, so a launch's span includes rank skew): report the
+    MEDIAN launch, max over ranks.  A back-to-back loop time is dominated by host launch skew for sub-ms messages."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    evs = []
     for _ in range(iters):
-        fn()
-    e1.record()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        evs.append((e0, e1))
     torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda")
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ts[len(ts) // 2]], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t[0])
 

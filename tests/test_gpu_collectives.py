@@ -275,3 +275,30 @@ def test_full_size_round_trip_property(bg, ref):
     finally:
         bg.set_tunable("comm_ctas", 8)
         w.close()
+
+
+@pytest.mark.parametrize("shard", [8, 4096 * 8 + 8])
+def test_reduce_scatter_adamw_epilogue(world, ref, shard):
+    """C2 with the AdamW epilogue == exact reduce-scatter followed by torch.optim.AdamW on the fp32 shard (3 steps)."""
+    n = world.n
+    g = torch.Generator(device="cpu").manual_seed(21 + shard)
+    pre, post = ref.fsdp_divide_factors(n)
+    params = [torch.randn(shard, generator=g) for _ in range(n)]
+    refs = [torch.nn.Parameter(p.clone().double()) for p in params]
+    opts = [torch.optim.AdamW([r], lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1) for r in refs]
+    dev_p = [p.clone().cuda() for p in params]
+    dev_m = [torch.zeros(shard, device="cuda") for _ in range(n)]
+    dev_v = [torch.zeros(shard, device="cuda") for _ in range(n)]
+    sym = world.sym(shard * n * 2)
+    for step in range(1, 4):
+        srcs = [torch.randn(shard * n, generator=g).to(torch.bfloat16) for _ in range(n)]
+        for r in range(n):
+            sym[r].view(torch.bfloat16, shard * n).copy_(srcs[r])
+        world.run(lambda r, c: c.reduce_scatter_adamw(world.group, sym[r], torch.bfloat16, dev_p[r], dev_m[r], dev_v[r], shard,
+                                                      1.0 / pre, 1.0 / post, 1e-2, 0.9, 0.95, 1e-8, 0.1, step))
+        exact = ref.reduce_scatter_acc(srcs, None, order="exact", accumulate=False, out_dtype=torch.float64)
+        for r in range(n):
+            refs[r].grad = exact[r].double()
+            opts[r].step()
+    for r in range(n):
+        torch.testing.assert_close(dev_p[r].cpu().double(), refs[r].detach(), rtol=2e-5, atol=2e-5)

@@ -45,3 +45,16 @@ def test_smoke_entry():
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import __graft_entry__ as ge
     ge.smoke()
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_fused_gemm_reduce_scatter(n):
+    """GEMM whose epilogue reduce-scatters over the TP group (partial tiles -> owner's HBM -> tile reducer) vs
+    cuBLAS + NCCL reduce_scatter, at the Llama-3-8B row-parallel shapes; needs n real GPUs."""
+    _need(n)
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
+                          "127.0.0.1", "--master-port", str(29800 + n), os.path.join(root, "scripts", "test_fused_gemm_rs.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "FUSED_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
