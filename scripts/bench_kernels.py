@@ -64,6 +64,47 @@ def cast():
     comm.close()
 
 
+def attn():
+    """K3 is a library call in the reference (flash-attn 2); compare the attention libraries present in the image."""
+    import torch.nn.functional as F
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+    b, s, n, ng, d = 1, 8192, 32, 8, 128
+    q = torch.randn(b, s, n, d, device="cuda", dtype=BF, requires_grad=True)
+    k = torch.randn(b, s, ng, d, device="cuda", dtype=BF, requires_grad=True)
+    v = torch.randn(b, s, ng, d, device="cuda", dtype=BF, requires_grad=True)
+    do = torch.randn(b, s, n, d, device="cuda", dtype=BF)
+    fl_f = 4.0 * b * s * s * n * d / 2
+    results = {}
+
+    def run(name, fwd):
+        try:
+            out = fwd()
+            t_f = timeit(fwd)
+            def fb():
+                o = fwd()
+                o.backward(do, retain_graph=False)
+                q.grad = k.grad = v.grad = None
+            t_fb = timeit(fb)
+            results[name] = out.detach()
+            print(json.dumps({"bench": "attention", "impl": name, "fwd_ms": round(t_f, 3), "fwd_tflops": round(fl_f / t_f / 1e9, 1),
+                              "fwd_bwd_ms": round(t_fb, 3), "fwd_bwd_tflops": round(3.5 * fl_f / t_fb / 1e9, 1)}), flush=True)
+        except Exception as e:  # noqa: BLE001
+            print(json.dumps({"bench": "attention", "impl": name, "error": str(e)[:300]}), flush=True)
+
+    from flash_attn import flash_attn_func
+    run("flash_attn2", lambda: flash_attn_func(q, k, v, causal=True))
+    for be_name, be in (("sdpa_cudnn", SDPBackend.CUDNN_ATTENTION), ("sdpa_flash", SDPBackend.FLASH_ATTENTION)):
+        def f(be=be):
+            with sdpa_kernel(be):
+                return F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True,
+                                                      enable_gqa=True).transpose(1, 2)
+        run(be_name, f)
+    if "flash_attn2" in results:
+        for name, o in results.items():
+            print(json.dumps({"bench": "attention_parity", "impl": name,
+                              "max_abs_diff_vs_flash_attn2": float((o.float() - results["flash_attn2"].float()).abs().max())}), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "cast"]
     print(json.dumps({"device": torch.cuda.get_device_name(0)}))
