@@ -73,6 +73,7 @@ class CudaBackend:
         self.p2p_stream = torch.cuda.Stream(device=self.device)
         self.fuse_stream = torch.cuda.Stream(device=self.device)
         self.fuse_gemm_rs = os.environ.get("HGB_FUSE_GEMM_RS", "1") != "0"
+        self.attn_impl = os.environ.get("HGB_ATTN", "cudnn")
         self._staging = {}  # group ranks -> SymBuffer
         self._scratch = {}
         self.gemm_profile = None   # bench.py: list of (start_event, end_event, flops) while timing the dominant kernel
@@ -409,9 +410,22 @@ class CudaBackend:
         # the reference casts cos/sin to the activation dtype before applying them (apply_rotary_pos_emb)
         return torch.cos(freqs).to(dtype).float().contiguous(), torch.sin(freqs).to(dtype).float().contiguous()
 
+    def attention(self, q, k, v, causal, softmax_scale):
+        """Attention is a LIBRARY call, as in the reference (transformer.py:495 calls flash-attn; K3 is not a collective and
+        is outside the hot-path scope).  On B200 the fastest library in the image is cuDNN's fused SDPA (tcgen05 kernels:
+        measured 1459 TFLOP/s fwd vs 370 for flash-attn 2's sm80-class kernels, profiles/r01_attention_libraries.jsonl), reached
+        through torch SDPA; HGB_ATTN=flash selects flash-attn 2.  q [b,s,n,d], k/v [b,s,ng,d] (GQA un-expanded).  Differentiable."""
+        if self.attn_impl != "cudnn":
+            return None
+        import torch.nn.functional as F
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+        with sdpa_kernel([SDPBackend.CUDNN_ATTENTION]):
+            o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=causal,
+                                               scale=softmax_scale, enable_gqa=k.shape[2] != q.shape[2])
+        return o.transpose(1, 2)
+
     def attention_fwd(self, q, k, v, causal, softmax_scale):
-        """flash-attn library call, as the reference (transformer.py:495 flash_attn_varlen_func; K3 is not a
-        collective and stays a dependency).  q [b,s,n,d], k/v [b,s,ng,d] (GQA un-expanded)."""
+        """flash-attn 2 library call (the reference's choice); used when HGB_ATTN=flash."""
         from flash_attn.flash_attn_interface import _flash_attn_forward
         out, lse, _, rng = _flash_attn_forward(q, k, v, 0.0, softmax_scale, causal=causal, window_size_left=-1,
                                                window_size_right=-1, softcap=0.0, alibi_slopes=None, return_softmax=False)

@@ -7,7 +7,7 @@ Data flow of one attention block (SBH activations, flash layout inside):
     hidden [s,b,h] -> ColumnParallelLinear (tcgen05 GEMM, TP/SP comm in staging)           -> mixed [s,b,ng*(r+2)*hn]
     -> ONE kernel: QKV split + RoPE + SBH->BSND relayout (K/V stay un-expanded for GQA)        -> q,k,v
     -> [Ulysses: ONE pull all-to-all for q,k,v with the head/seq transpose folded in]
-    -> flash-attn (library, as the reference)  -> [Ulysses: inverse all-to-all]               -> context [s,b,np*hn]
+    -> attention LIBRARY call (cuDNN SDPA; the reference calls flash-attn) -> [Ulysses: inverse all-to-all] -> context [s,b,np*hn]
     -> RowParallelLinear (GEMM into staging -> all-reduce | reduce-scatter over NVLink)      -> out [s,b,h]
 The reference runs split, repeat_interleave, 2x rope, 3x rearrange().contiguous() and, per Ulysses tensor, a permute
 copy + NCCL all_to_all + a second permute copy (transformer.py:731-767,842-867,1934-1962).
@@ -133,6 +133,13 @@ class _FlashAttnFn(torch.autograd.Function):
         return dq, dk, dv, None, None
 
 
+def _attention(q, k, v, causal, scale):
+    be = get_backend()
+    fn = getattr(be, "attention", None)
+    out = fn(q, k, v, causal, scale) if fn is not None else None   # differentiable library call (cuDNN SDPA on B200)
+    return out if out is not None else _FlashAttnFn.apply(q, k, v, causal, scale)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # layer modules
 # ---------------------------------------------------------------------------------------------------------------
@@ -203,10 +210,10 @@ class ParallelAttention(nn.Module):
                 rep = self.np_local // self.ng_local
                 k, v = k.repeat_interleave(rep, dim=2), v.repeat_interleave(rep, dim=2)
             q, k, v = _UlyssesFn.apply(self.sp_group, True, q, k, v)       # [b, s, n/p, hn]
-            ctxt = _FlashAttnFn.apply(q, k, v, causal, self.softmax_scale)
+            ctxt = _attention(q, k, v, causal, self.softmax_scale)
             (ctxt,) = _UlyssesFn.apply(self.sp_group, False, ctxt)         # [b, s/p, n, hn]
         else:
-            ctxt = _FlashAttnFn.apply(q, k, v, causal, self.softmax_scale)  # [b, s, np, hn]
+            ctxt = _attention(q, k, v, causal, self.softmax_scale)          # [b, s, np, hn]
         b, s = ctxt.shape[0], ctxt.shape[1]
         ctxt = ctxt.reshape(b, s, -1).transpose(0, 1).contiguous()          # "b s h d -> s b (h d)"
         return self.dense(ctxt)

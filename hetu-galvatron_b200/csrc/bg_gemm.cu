@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_con
         const bool issuer = threadIdx.x == 4 * 32;
         int acc = 0; uint32_t acc_phase = 0;
         int buf = 0;
+        uint32_t* prev_flag = nullptr;                // fused scatter: arrival counter of the tile whose stores are in flight
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const TileCoord tc = tile_of(t, m_blocks, n_blocks);
             mbar_wait(smem_u32(tmem_full + acc), acc_phase);
@@ -309,17 +310,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_con
             }
             if constexpr (kScatter) {
                 if (issuer) {
-                    // the whole tile has been handed to the TMA: wait until the peer stores are complete, then publish it
-                    tma_store_wait_all<0>();
+                    // Publish the PREVIOUS tile: every bulk group except this tile's (<= 4 chunks) has completed, so its peer
+                    // stores are done -- no stall on this tile's NVLink latency.
+                    if (prev_flag != nullptr) {
+                        asm volatile("cp.async.bulk.wait_group %0;" ::"n"(BLOCK_N / kStoreCols) : "memory");
+                        __threadfence_system();
+                        asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(prev_flag) : "memory");
+                    }
                     const int row0 = tc.m * BLOCK_M, owner = row0 / sp.rows_per_rank;
-                    const int local_tile = ((row0 - owner * sp.rows_per_rank) / BLOCK_M) * n_blocks + tc.n;
-                    __threadfence_system();
-                    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(sp.flags[owner] + local_tile) : "memory");
+                    prev_flag = sp.flags[owner] + ((row0 - owner * sp.rows_per_rank) / BLOCK_M) * n_blocks + tc.n;
                 }
             }
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
-        if (issuer) tma_store_wait_all<0>();
+        if (issuer) {
+            tma_store_wait_all<0>();
+            if constexpr (kScatter) {
+                if (prev_flag != nullptr) {
+                    __threadfence_system();
+                    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(prev_flag) : "memory");
+                }
+            }
+        }
     }
 
     tc_fence_before();
@@ -446,15 +458,21 @@ __global__ void __launch_bounds__(256) tile_reduce_kernel(const __nv_bfloat16* _
         for (int i = threadIdx.x; i < rows * vec_per_row; i += blockDim.x) {
             const int r = i / vec_per_row, c = i - r * vec_per_row;
             const size_t off = (size_t)(row0 + r) * N + col0 + c * 8;
+            uint4 in[BG_MAX_PEERS];
+#pragma unroll
+            for (int src = 0; src < BG_MAX_PEERS; ++src)
+                if (src < p) in[src] = ld16_stream(partial + (size_t)src * rows_per_rank * N + off);
             float acc[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-            for (int src = 0; src < p; ++src) {
-                float f[8];
-                unpack8(ld16_stream(partial + (size_t)src * rows_per_rank * N + off), f);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] += f[e];
-            }
+            for (int src = 0; src < BG_MAX_PEERS; ++src)
+                if (src < p) {
+                    float f[8];
+                    unpack8(in[src], f);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[e] += f[e];
+                }
             st16(out + off, pack8(acc));
         }
         __syncthreads();
@@ -504,7 +522,7 @@ int bg_gemm_scatter_launch(const void* a, const void* b, long long m, long long 
     const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
     const int local_tiles = (rows_per_rank / BLOCK_M) * n_blocks;
     // reducer first (it only waits on flags), so it is resident when the first tiles land
-    int rgrid = local_tiles < 32 ? local_tiles : 32;
+    int rgrid = local_tiles < 2 * g_num_sms ? local_tiles : 2 * g_num_sms;   // co-resident with the GEMM CTAs (256 thr, no smem)
     tile_reduce_kernel<<<rgrid, 256, 0, st_reduce>>>((const __nv_bfloat16*)partial_ptrs[me], flag_ptrs[me], (__nv_bfloat16*)out, p,
                                                      rows_per_rank, (int)n, n_blocks, local_tiles, timeout_ns, err_dev);
     BG_CHECK_LAUNCH();

@@ -89,6 +89,7 @@ def main():
     ap.add_argument("--memory-gb", type=int, default=170)
     ap.add_argument("--seq", type=int, default=8192)
     ap.add_argument("--gpus", type=int, nargs="*", default=[1, 2, 4, 8])
+    ap.add_argument("--debug-memory", action="store_true", help="print the engine's per-layer memory model for the dp-only strategy")
     opts = ap.parse_args()
 
     dp_dir = build_dp_core()
@@ -138,6 +139,13 @@ def main():
         engine = GalvatronSearchEngine(args)
         engine.set_search_engine_info(work, [{"hidden_size": 4096, "seq_len": opts.seq, "layer_num": 32}], model_name)
         engine.initialize_search_engine()
+        if opts.debug_memory:
+            from galvatron.core.search_engine.cost_model import MemoryCostModel
+            for strat in ([1, 1, n, {}] if n == 1 else [1, 1, n, {"fsdp": 0}], [1, 1, n, {"cpt": 1}] if n == 1 else [1, 1, n, {"fsdp": 0, "cpt": 1}]):
+                m = MemoryCostModel(strat, global_batch_size=8 * n, mbsz=1, min_tp=1, max_tp=1, model_args=engine.model_args_list[0],
+                                    train_args=engine.train_args_list[0], parallel_args=engine.parallel_args_list[0],
+                                    profile_model_args=engine.profile_model_args_list[0]).get_memory_cost()
+                print("MEMDEBUG", strat, {k: (v if not isinstance(v, dict) else v) for k, v in m.items()})
         thr = engine.parallelism_optimization()
         files = glob.glob(os.path.join(out_dir, "*.json"))
         if not files:
