@@ -54,6 +54,14 @@ WORLD2 = {
 WORLD4 = {
     "tp2_dp2_sp_zero2": dict(global_tp_deg=2, vocab_tp=2, sequence_parallel=True, default_dp_type="zero2", chunks=2),
     "pp2_tp2_1f1b": dict(pp_deg=2, global_tp_deg=2, vocab_tp=2, chunks=2, pipeline_type="pipedream_flush"),
+    # BASELINE config (3) shape: PP2 x TP2 x ZeRO-2 with Megatron-SP, 1F1B-flush, 4 microbatches
+    "baseline3_pp2_tp2_sp_zero2": dict(pp_deg=2, global_tp_deg=2, vocab_tp=2, sequence_parallel=True, default_dp_type="zero2",
+                                       chunks=4, pipeline_type="pipedream_flush", global_train_batch_size=8),
+    # BASELINE config (4) shape: Ulysses sequence parallel x data parallel (grads reduce over DP x SP)
+    "baseline4_ulysses2_dp2": dict(global_tp_deg=2, use_ulysses=True, sequence_parallel=True, vocab_tp=2, default_dp_type="zero2",
+                                   chunks=2, global_train_batch_size=8),
+    # BASELINE config (5) shape: ZeRO-3 on every layer + activation checkpointing
+    "baseline5_zero3_ckpt_dp4": dict(sdp=1, global_checkpoint=1, embed_sdp=1, chunks=1, global_train_batch_size=8),
     "hybrid_mixed": dict(sequence_parallel=True, _spec={"n_kv_heads": 4},
                          _strategy_json={"pp_deg": 1, "tp_sizes_enc": "2,4", "tp_consecutive_flags": "1,1", "dp_types_enc": "1,0",
                                          "use_sp": "1,0", "checkpoint": "0,1", "global_bsz": 8, "chunks": 2,
