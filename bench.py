@@ -105,6 +105,23 @@ def measured_peaks():
     return 1400.0, "B200_PROFILING.md fallback (sustained ~1.4 PFLOP/s)"
 
 
+def ncu_gemm_traffic(flops_per_launch_avg):
+    """DRAM bytes per (average) GEMM launch from the committed `ncu --set full` capture: the capture holds three launches of
+    known shape; their bytes-per-FLOP ratio is applied to the average launch of the timed region."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_gemm_full_summary.json")
+    try:
+        with open(path) as f:
+            launches = json.load(f)["launches"]
+        to_bytes = lambda s: float(s.split()[0]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[s.split()[1]]  # noqa: E731
+        total = sum(to_bytes(l["dram__bytes_read.sum"]) + to_bytes(l["dram__bytes_write.sum"]) for l in launches)
+        # the three captured launches: gate/up dgrad [8192x28672]x[28672x4096], o-proj wgrad and dgrad [8192|4096 x 4096 x 4096|8192]
+        flops = 2.0 * 8192 * 4096 * (28672 + 4096 + 4096)
+        return round(total / flops * flops_per_launch_avg), ("dram__bytes_read+write of 3 captured launches (profiles/r01_ncu_gemm_full_summary.json) "
+                                                            "scaled by FLOPs to the average launch of this run")
+    except Exception:  # noqa: BLE001
+        return None, "no ncu capture found"
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def build_model(opts, strategy, backend=None):
     import torch
@@ -228,8 +245,10 @@ def run_ours(opts):
     ms_e2e, _, loss_e2e = timed(resident=False)
     clocks = sampler.stop() if rank == 0 else None
     torch.cuda.synchronize()
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
-    gemm_flops = sum(f for _, _, f in prof)
+    gemm_ms = sum(rec[0].elapsed_time(rec[1]) for rec in prof)
+    gemm_flops = sum(rec[2] for rec in prof)
+    gemm_bytes = sum(rec[3] for rec in prof)
+    traffic, traffic_note = ncu_gemm_traffic(gemm_flops / max(1, len(prof)))
     peak, peak_src = measured_peaks()
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     h2d = 2 * (args.global_train_batch_size // dp_size) * config.max_position_embeddings * 8
@@ -249,7 +268,8 @@ def run_ours(opts):
                 "d2h_bytes_per_step": 4 * max(1, strategy["chunks"]), "ms_per_step": round(ms_e2e / K, 3)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
-                     "frac": round(achieved / peak, 4) if peak else None, "traffic": None, "kernel": "gemm_bf16_kernel (tcgen05/TMEM/TMA)",
+                     "frac": round(achieved / peak, 4) if peak else None, "traffic": traffic, "traffic_note": traffic_note,
+                     "algorithmic_bytes_per_launch_avg": gemm_bytes / max(1, len(prof)), "kernel": "gemm_bf16_kernel (tcgen05/TMEM/TMA)",
                      "launches": len(prof), "kernel_ms_per_step": round(gemm_ms / K, 3), "share_of_step": round(gemm_ms / ms_res, 4),
                      "flops_per_launch_avg": gemm_flops / max(1, len(prof)), "peak_source": peak_src},
         "clocks": clocks, "loss": {"resident": loss_res, "e2e": loss_e2e},

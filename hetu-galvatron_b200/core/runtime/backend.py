@@ -322,7 +322,7 @@ class CudaBackend:
             e0.record()
             self.bg.gemm_bf16(a, b, out, m_, n_, k_, code, accumulate=accumulate)
             e1.record()
-            self.gemm_profile.append((e0, e1, 2.0 * m_ * n_ * k_))
+            self.gemm_profile.append((e0, e1, 2.0 * m_ * n_ * k_, 2.0 * (m_ * k_ + k_ * n_ + m_ * n_ * (2 if accumulate else 1))))
         else:
             self.bg.gemm_bf16(a, b, out, m_, n_, k_, code, accumulate=accumulate)
         return out
