@@ -41,11 +41,21 @@ def main():
     be.reserve_staging(grp, M * N * 2 * 2)
     be.exchange()
     ok_all = True
+    # library handles (cuBLAS workspace, NCCL channels) are created BEFORE any peer-waiting kernel is in flight
+    warm = torch.randn(256, 256, device="cuda").to(BF)
+    torch.matmul(warm, warm)
+    dist.all_reduce(torch.zeros(8, device="cuda"))
+    torch.cuda.synchronize()
     for layout, K in (("tn", 14336 // world), ("nn", 6144 // world), ("tn", 4096 // world)):
         torch.manual_seed(7 + rank)
         a = (torch.randn(M, K, device="cuda") * 0.5).to(BF)
         b = (torch.randn((N, K) if layout == "tn" else (K, N), device="cuda") * 0.5).to(BF)
         out = be.gemm_reduce_scatter(a, b, layout, grp)
+        try:
+            torch.cuda.synchronize()
+        except RuntimeError as exc:
+            print("rank %d: fused GEMM+RS failed (%s), error flag %s" % (rank, str(exc).splitlines()[0], be.comm.error_flag()), file=sys.stderr, flush=True)
+            raise
         full = torch.matmul(a, b.t() if layout == "tn" else b)
         ref = torch.empty(M // world, N, device="cuda", dtype=BF)
         dist.reduce_scatter_tensor(ref, full)
