@@ -46,6 +46,7 @@ SIGNATURES = {
     "bg_arena_import": (_i, [_vp, _i, _vp]),
     "bg_arena_attach_local": (_i, [_vp, _i, _vp]),
     "bg_ctx_error_flag": (_i, [_vp, _c.POINTER(_i)]),
+    "bg_ctx_error_info": (_i, [_vp, _c.POINTER(_i)]),
     "bg_group_create": (_i, [_vp, _c.POINTER(_i), _i, _c.POINTER(_i)]),
     "bg_group_info": (_i, [_vp, _i, _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i)]),
     "bg_build_groups": (_i, [_i, _i, _i, _i, _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i),
@@ -69,7 +70,7 @@ SIGNATURES = {
     "bg_ce_sumexp": (_i, [_vp, _i, _vp, _vp, _vp, _ll, _ll, _ll, _vp]),
     "bg_ce_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _ll, _ll, _ll, _vp]),
     "bg_gemm_bf16": (_i, [_vp, _vp, _vp, _ll, _ll, _ll, _i, _i, _vp]),
-    "bg_gemm_reduce_scatter": (_i, [_vp, _i, _i, _vp, _vp, _ll, _ll, _ll, _i, _c.POINTER(_sz), _c.POINTER(_sz), _vp, _vp, _vp]),
+    "bg_gemm_reduce_scatter": (_i, [_vp, _i, _i, _vp, _vp, _ll, _ll, _ll, _i, _c.POINTER(_sz), _c.POINTER(_sz), _vp, _vp]),
 }
 
 _lib = None
@@ -329,12 +330,12 @@ class BgComm:
         check(lib().bg_all_to_all_rows(self._ctx, self.group_id(group), lane, arr, len(descs), dtype_code(dtype),
                                        _stream_ptr(stream)))
 
-    def gemm_reduce_scatter(self, group, a, b, m, n, k, layout, partial, partial_byte_offset, flags_byte_offset, out, reduce_stream,
+    def gemm_reduce_scatter(self, group, a, b, m, n, k, layout, partial, partial_byte_offset, flags_byte_offset, out,
                             lane=LANE_ACT, stream=None):
         """C = A op B reduce-scattered along M over ``group`` in one fused operation (partial tiles -> owner's HBM)."""
         check(lib().bg_gemm_reduce_scatter(self._ctx, self.group_id(group), lane, _ptr(a), _ptr(b), int(m), int(n), int(k), int(layout),
                                            partial.sub(partial_byte_offset), partial.sub(flags_byte_offset), _ptr(out),
-                                           _stream_ptr(stream), _vp(reduce_stream.cuda_stream)))
+                                           _stream_ptr(stream)))
 
     def p2p_send(self, peer_rank, dst_offset, src, flag_id, stream=None):
         check(lib().bg_p2p_send(self._ctx, int(peer_rank), int(dst_offset), _ptr(src), src.numel() * src.element_size(),
@@ -350,6 +351,13 @@ class BgComm:
         out = _i()
         check(lib().bg_ctx_error_flag(self._ctx, ctypes.byref(out)))
         return out.value
+
+    def error_info(self):
+        """The device-side timeout record: status, kind (1 signalling / 2 waiting for a peer, 3 fused-GEMM tile reducer),
+        CTA, thread-or-tile, value last seen, and two kind-specific integers."""
+        out = (_i * 8)()
+        check(lib().bg_ctx_error_info(self._ctx, out))
+        return list(out)
 
 
 # ---- local ops (no communicator needed) ---------------------------------------------------------------------

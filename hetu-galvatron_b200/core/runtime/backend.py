@@ -71,7 +71,6 @@ class CudaBackend:
         self.unshard_stream = torch.cuda.Stream(device=self.device)
         self.reduce_stream = torch.cuda.Stream(device=self.device)
         self.p2p_stream = torch.cuda.Stream(device=self.device)
-        self.fuse_stream = torch.cuda.Stream(device=self.device)
         self.fuse_gemm_rs = os.environ.get("HGB_FUSE_GEMM_RS", "1") != "0"
         self.attn_impl = os.environ.get("HGB_ATTN", "cudnn")
         self._staging = {}  # group ranks -> SymBuffer
@@ -139,6 +138,8 @@ class CudaBackend:
     def unit_unshard(self, unit):
         """C1 on the unshard stream: all-gather + fp32->bf16 cast of the unit's flat parameter."""
         with torch.cuda.stream(self.unshard_stream):
+            if getattr(unit, "_w_wait_event", None) is not None:    # pooled slot: its previous occupant's last use
+                self.unshard_stream.wait_event(unit._w_wait_event)
             if unit.dp_type == "ddp":
                 self.cast(unit.flat_param.data, unit.w_flat)
             else:
@@ -190,6 +191,21 @@ class CudaBackend:
 
     def finish_reductions(self):
         torch.cuda.current_stream().wait_stream(self.reduce_stream)
+
+    # ---- events (ordering between successive occupants of a pooled zero3 buffer) ------------------------------------------
+    def record_event(self):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        return ev
+
+    def reduce_done_event(self):
+        ev = torch.cuda.Event()
+        ev.record(self.reduce_stream)
+        return ev
+
+    def wait_event(self, ev):
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
 
     def make_stage_link(self, my_rank, peer_rank, max_bytes, send_flag_base, recv_flag_base):
         from .pipeline.pipeline import _StageLink
@@ -346,8 +362,7 @@ class CudaBackend:
         n_ = b.shape[0] if code == 0 else b.shape[1]
         buf = self.staging(group, m_ * n_ * 2)
         out = torch.empty(m_ // group.size, n_, dtype=torch.bfloat16, device=a.device)
-        self.comm.gemm_reduce_scatter(group, a, b, m_, n_, k_, code, buf, 0, buf.data_bytes, out, self.fuse_stream)
-        torch.cuda.current_stream().wait_stream(self.fuse_stream)
+        self.comm.gemm_reduce_scatter(group, a, b, m_, n_, k_, code, buf, 0, buf.data_bytes, out)
         return out
 
     def rmsnorm_fwd(self, x, weight, eps):

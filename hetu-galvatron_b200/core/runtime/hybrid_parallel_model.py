@@ -17,7 +17,7 @@ from .backend import get_backend
 from .comm_groups import gen_comm_groups
 from .hybrid_parallel_config import (check_hp_config, get_chunks, hp_config_whole_model, layer_shapes_dtypes_whole_model,
                                      mixed_precision_dtype)
-from .parallel import wrap_modules_relocation
+from .parallel import finalize_pools, wrap_modules_relocation
 
 
 class GalvatronModel(nn.Module):
@@ -160,6 +160,7 @@ def construct_hybrid_parallel_model_api(model, model_config, training_args, hybr
     # exchange of arena offsets for the whole job (replaces all NCCL communicator bootstraps)
     _reserve_activation_staging(be, args, info, hp_whole, hp_model, tp_groups_whole, sp_groups_whole, split_tp_sp_cp_groups_whole,
                                 allgather_tp_sp_cp_groups_whole, fused_allgather_groups_whole, fused_split_groups_whole)
+    finalize_pools(be)
     be.exchange()
 
     gm = GalvatronModel(hp_model)

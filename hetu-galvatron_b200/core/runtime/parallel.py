@@ -11,8 +11,9 @@ layer whose observable semantics are the reference's:
   ddp         full                 local cast                       all-reduce          (NO_SHARD)
   zero2       1/d shard            all-gather+cast once per step    reduce-scatter      (SHARD_GRAD_OP)
   zero3       1/d shard            all-gather+cast fwd and bwd*     reduce-scatter      (FULL_SHARD)
-  (* the gathered copy is kept while its buffer has not been reclaimed, so the second gather is skipped when memory
-     allows; comm volume <= the reference's.)
+  (* zero3 layers gather into a small rotating pool of peer-visible buffers (``SlotPool``), released after every forward
+     and backward exactly where FSDP reshards; a released copy stays valid until its slot is reclaimed, so the second gather
+     is skipped when the pool is large enough -- comm volume <= the reference's, memory = pool size, not model size.)
 
   * gradients accumulate UNSHARDED in bf16 across microbatches and are reduced once per step, on the last microbatch
     (default ``async_grad_reduce``; grad_reduce.py:47-64,177-198) -- but each layer's reduce-scatter is launched as soon
@@ -40,11 +41,89 @@ def fsdp_divide_factors(world_size):
     return float(factor), world_size / float(factor)
 
 
+class _Slot:
+    __slots__ = ("buf", "owner", "version", "free_event", "index")
+
+    def __init__(self, buf, index):
+        self.buf, self.index, self.owner, self.version, self.free_event = buf, index, None, None, None
+
+
+class SlotPool:
+    """Rotating peer-visible buffers shared by the zero3 units of one (group, dtype, role): what FSDP's alloc/free of the
+    padded unsharded flat parameter (``_flat_param.py`` _alloc_padded_unsharded_flat_param / _free_unsharded_flat_param)
+    becomes when the memory must stay peer-mapped.  Every member of the group walks the same program, so the same slot
+    index is chosen everywhere and the peers' pushes land in the matching slot.  Ordering between successive occupants is
+    by CUDA events on the owner's streams plus the collective's own entry barrier across ranks."""
+
+    def __init__(self, be, group, dtype, n_slots, role):
+        self.be, self.group, self.dtype, self.n_slots, self.role = be, group, dtype, int(n_slots), role
+        self.max_elems = 0
+        self.slots = None
+        self.free = []          # release order: oldest first
+        self.held = {}          # id(unit) -> slot
+        self.n_gather_skipped = 0
+
+    def register(self, unit):
+        assert self.slots is None, "zero3 pool already allocated"
+        self.max_elems = max(self.max_elems, unit.padded)
+
+    def finalize(self):
+        if self.slots is None:
+            esz = torch.empty((), dtype=self.dtype).element_size()
+            self.slots = [_Slot(self.be.sym_alloc(self.group, self.max_elems * esz), i) for i in range(self.n_slots)]
+            self.free = list(self.slots)
+
+    def nbytes(self):
+        return self.n_slots * self.max_elems * torch.empty((), dtype=self.dtype).element_size()
+
+    def acquire(self, unit, version=None, demand=True):
+        """-> (slot, cached).  ``cached``: the slot still holds this unit's data of this ``version`` (no gather needed).
+        Without a free slot a demand acquire evicts a prefetched, not-yet-used occupant; a prefetch just gives up (None)."""
+        self.finalize()
+        if version is not None:
+            for i, s in enumerate(self.free):
+                if s.owner is unit and s.version == version:
+                    del self.free[i]
+                    self.held[id(unit)] = s
+                    self.n_gather_skipped += 1
+                    return s, True
+        if not self.free:
+            if not demand:
+                return None, False
+            victim = next((s.owner for s in self.held.values() if s.owner._in_use == 0 and s.owner is not unit), None)
+            if victim is None:
+                raise RuntimeError("zero3 %s pool of %d slots exhausted by layers in use: raise --zero3_pool_slots" % (self.role, self.n_slots))
+            victim.evict(self.role)
+        s = self.free.pop(0)
+        s.owner, s.version = unit, version
+        self.held[id(unit)] = s
+        return s, False
+
+    def release(self, unit, event):
+        s = self.held.pop(id(unit))
+        s.free_event = event
+        self.free.append(s)
+
+
+def get_pool(be, group, dtype, n_slots, role):
+    pools = be.__dict__.setdefault("_zero3_pools", {})
+    key = (tuple(group.ranks), dtype, role)
+    if key not in pools:
+        pools[key] = SlotPool(be, group, dtype, n_slots, role)
+    return pools[key]
+
+
+def finalize_pools(be):
+    """Allocate every registered pool (before ``backend.exchange()``)."""
+    for pool in be.__dict__.get("_zero3_pools", {}).values():
+        pool.finalize()
+
+
 class ShardedUnit:
     """One layer's flat parameter, sharded over ``group`` (what an FSDP unit is in the reference)."""
 
     def __init__(self, module, group, dp_type, name="", tp_group=None, param_dtype=torch.bfloat16, reduce_in_fp32=False,
-                 sequence_parallel=False, init_seed=None):
+                 sequence_parallel=False, init_seed=None, pool_slots=0, pool_grads=False):
         assert dp_type in _DP_TYPES, dp_type
         be = get_backend()
         self.be, self.module, self.group, self.dp_type, self.name = be, module, group, dp_type, name
@@ -87,26 +166,37 @@ class ShardedUnit:
         self.fused_opt = None          # set by FusedShardedAdamW: the reduction's epilogue applies the update
 
         # ---- peer-visible flat buffers: W (gathered params) and G (unsharded grads) --------------------------------
+        # zero3 layers take theirs from a rotating pool (``pool_slots`` > 0): memory is the pool's, not the model's.
         esz = torch.empty((), dtype=param_dtype).element_size()
         gsz = torch.empty((), dtype=self.reduce_dtype).element_size()
-        self.W = be.sym_alloc(group, self.padded * esz)
-        self.G = be.sym_alloc(group, self.padded * gsz)
-        self.w_flat = self.W.view(param_dtype, self.padded)
-        self.g_flat = self.G.view(self.reduce_dtype, self.padded)
-        self.g_flat.zero_()
-        self.w_flat.copy_(full.to(param_dtype))  # valid until the first optimizer step
-        for p, off, n in zip(params, self.offsets, self.numels):
-            shape = p.shape
-            p.data = self.w_flat[off:off + n].view(shape)
-            p._bg_grad = self.g_flat[off:off + n].view(shape)
+        self.shapes = [p.shape for p in params]
+        pooled = dp_type == "zero3" and d > 1 and pool_slots > 0
+        self.w_pool = get_pool(be, group, param_dtype, pool_slots, "param") if pooled else None
+        self.g_pool = get_pool(be, group, self.reduce_dtype, max(2, pool_slots - 1), "grad") if pooled and pool_grads else None
+        self.W = self.G = self.w_flat = self.g_flat = None
+        self._w_version, self._in_use, self._w_wait_event = 0, 0, None
+        for p in params:
             p._bg_unit = self
+        if self.w_pool is None:
+            self._bind_w(be.sym_alloc(group, self.padded * esz))
+            self.w_flat.copy_(full.to(param_dtype))  # valid until the first optimizer step
+        else:
+            self.w_pool.register(self)
+            placeholder = torch.empty(0, dtype=param_dtype, device=device)
+            for p in params:
+                p.data = placeholder       # FSDP's freed unsharded flat parameter
+        if self.g_pool is None:
+            self._bind_g(be.sym_alloc(group, self.padded * gsz))
+            self.g_flat.zero_()
+        else:
+            self.g_pool.register(self)
         del full
         self._ln_params = [p for p in params if getattr(p, "sequence_parallel", False)] if (
             sequence_parallel and tp_group is not None and tp_group.size > 1) else []
 
         self.prediv, self.postdiv = fsdp_divide_factors(d)
         self._started = set()          # params whose G slice holds this step's gradient
-        self._w_valid = True
+        self._w_valid = self.w_pool is None
         self._unshard_event = None
         self._reduced_this_step = False
         self._pending = False          # backward ran since the last reduction
@@ -141,25 +231,88 @@ class ShardedUnit:
         else:
             module.to(device)
 
+    def _bind_w(self, buf):
+        self.W = buf
+        self.w_flat = buf.view(self.param_dtype, self.padded)
+        for p, off, n, shape in zip(self.params, self.offsets, self.numels, self.shapes):
+            p.data = self.w_flat[off:off + n].view(shape)
+
+    def _bind_g(self, buf):
+        self.G = buf
+        self.g_flat = buf.view(self.reduce_dtype, self.padded)
+        for p, off, n, shape in zip(self.params, self.offsets, self.numels, self.shapes):
+            p._bg_grad = self.g_flat[off:off + n].view(shape)
+
     # ---- step protocol ------------------------------------------------------------------------------------------------
     def begin_step(self, params_changed=True):
         """Called once per training iteration before the first forward (the optimizer has updated the master)."""
         if params_changed:
+            self._w_version += 1
+            if self.w_pool is not None and self._w_valid:
+                self.reshard()
             self._w_valid = False
         self._reduced_this_step = False
         self._started.clear()
         self._pending = False
 
-    def unshard(self):
+    def unshard(self, prefetch=False):
         """Launch (once) the all-gather + fp32->bf16 cast of this layer's parameters on the unshard stream (C1)."""
         if self._w_valid:
             return
+        if self.w_pool is not None:
+            slot, cached = self.w_pool.acquire(self, self._w_version, demand=not prefetch)
+            if slot is None:
+                return                  # no free slot for a prefetch: gather on demand later
+            self._bind_w(slot.buf)
+            self._w_wait_event = slot.free_event   # the previous occupant's last use (its owner's compute stream)
+            if cached:
+                self._w_valid = True
+                return
         self.be.unit_unshard(self)
+        self._w_wait_event = None
         self._w_valid = True
         self.n_unshard += 1
 
     def wait_unshard(self):
         self.be.unit_wait_unshard(self)
+
+    def reshard(self):
+        """FULL_SHARD's free of the unsharded parameters after forward / backward (_runtime_utils.py _reshard): hand the slot
+        back; the copy stays usable until another layer reclaims it."""
+        if self.w_pool is None or not self._w_valid or self._in_use:
+            return
+        self.be.unit_wait_unshard(self)     # the releasing stream has then seen the gather it is about to order after
+        self.w_pool.release(self, self.be.record_event())
+        self._w_valid = False
+
+    def evict(self, role):
+        """Give a prefetched-but-unused slot back to the pool (called by the pool on a demand acquire)."""
+        assert role == "param" and self._in_use == 0
+        self.reshard()
+
+    def acquire_grads(self):
+        """zero3 with pooled gradients: take a G slot before this layer's backward writes its first wgrad."""
+        if self.g_pool is None or self.G is not None:
+            return
+        slot, _ = self.g_pool.acquire(self)
+        self.be.wait_event(slot.free_event)   # its previous occupant's reduce-scatter has read it (here and on the peers)
+        self._bind_g(slot.buf)
+
+    def release_grads(self):
+        if self.g_pool is None or self.G is None:
+            return
+        self.g_pool.release(self, self.be.reduce_done_event())
+        self.G = self.g_flat = None
+        for p in self.params:
+            p._bg_grad = None
+
+    def read_full_params(self):
+        """Clone of the gathered low-precision flat parameter (tests, checkpoint export)."""
+        self.unshard()
+        self.wait_unshard()
+        out = self.w_flat.clone()
+        self.reshard()
+        return out
 
     def grad_started(self, p):
         return id(p) in self._started
@@ -197,7 +350,12 @@ class ShardedUnit:
     def post_backward(self, sync_gradients):
         """After this layer's backward for one microbatch.  With ``sync_gradients`` launch the gradient reduction (C2/C3)."""
         self._collect_autograd_grads()
-        if not sync_gradients or not self._pending:
+        if not sync_gradients:
+            if self.g_pool is not None:
+                raise RuntimeError("pooled zero3 gradients need a reduction after every backward (chunks == 1 or --no_async_grad_reduce)")
+            return
+        if not self._pending:
+            self.release_grads()
             return
         be = self.be
         for p in self.params:               # a parameter that received no gradient this step must contribute zeros
@@ -215,6 +373,7 @@ class ShardedUnit:
         self._started.clear()
         self._pending = False
         self.n_reduce += 1
+        self.release_grads()
 
     def finish_step(self):
         """Make the optimizer (current stream) wait for this step's reductions."""
@@ -307,16 +466,25 @@ class DataParallelModule(nn.Module):
         super().__init__()
         self.module, self.unit, self.checkpoint = module, unit, checkpoint
         self.next_unit = None           # forward prefetch target (the next layer of the stage)
+        self.prev_unit = None           # backward prefetch target
         self.sync_gradients = True      # set per microbatch by the schedule (PipelineParallel.set_last_batch)
         self._fired = True              # did _post_backward run during the current backward_step?
 
     def _pre_backward(self):
-        self.unit.unshard()
-        self.unit.wait_unshard()
+        unit = self.unit
+        unit.unshard()
+        if self.prev_unit is not None:
+            self.prev_unit.unshard(prefetch=True)   # backward prefetch: the previous layer's re-gather overlaps this backward
+        unit.wait_unshard()
+        unit._in_use += 1
+        unit.acquire_grads()
 
     def _post_backward(self):
         self._fired = True
-        self.unit.post_backward(self.sync_gradients)
+        unit = self.unit
+        unit.post_backward(self.sync_gradients)
+        unit._in_use = max(0, unit._in_use - 1)
+        unit.reshard()
 
     def arm_backward(self):
         """Called by the schedule right before ``autograd.backward`` of one microbatch."""
@@ -332,8 +500,16 @@ class DataParallelModule(nn.Module):
         unit = self.unit
         unit.unshard()
         if self.next_unit is not None:
-            self.next_unit.unshard()    # prefetch: the next layer's all-gather overlaps this layer's compute
+            self.next_unit.unshard(prefetch=True)   # the next layer's all-gather overlaps this layer's compute
         unit.wait_unshard()
+        unit._in_use += 1
+        try:
+            return self._forward(inputs, kwargs)
+        finally:
+            unit._in_use -= 1
+            unit.reshard()              # zero3: free the gathered copy (FULL_SHARD reshards after forward)
+
+    def _forward(self, inputs, kwargs):
         grad_mode = torch.is_grad_enabled()
         if self.checkpoint and grad_mode:
             # a dummy grad-requiring input keeps the node alive when no activation input requires grad

@@ -175,16 +175,19 @@ class PipelineParallel(nn.Module):
         assert self.total_model_len == len(dp_types) == len(dp_groups) == len(module_types)
         s0, s1 = self.stage_start_idx, self.stage_end_idx
         wrapped = []
+        # zero3 gradients can share a pool only when every backward is followed by its reduction
+        pool_grads = self.chunks == 1 or not args.async_grad_reduce
         for i, module in zip(range(s0, s1), self.model_cur_stage):
             dp_type = {0: args.default_dp_type, 1: "zero3"}[dp_types[i]]
             tp_group = None if tp_groups is None else tp_groups[i]
             unit = ShardedUnit(module, dp_groups[i], dp_type, name="%s_%d" % (module_types[i], i), tp_group=tp_group,
                                param_dtype=mixed_precision, reduce_in_fp32=args.reduce_in_fp32,
-                               sequence_parallel=self.sequence_parallel, init_seed=args.seed + 1000 * i)
+                               sequence_parallel=self.sequence_parallel, init_seed=args.seed + 1000 * i,
+                               pool_slots=int(getattr(args, "zero3_pool_slots", 0)), pool_grads=pool_grads)
             self.units.append(unit)
             wrapped.append(DataParallelModule(module, unit, checkpoint=False))
         for a, b in zip(wrapped[:-1], wrapped[1:]):
-            a.next_unit = b.unit
+            a.next_unit, b.prev_unit = b.unit, a.unit
         self.model_cur_stage = PipeSequential(*wrapped)
 
     def gen_sp_layernorm_info(self, *a, **k):

@@ -49,8 +49,6 @@ struct bg_ctx {
     int* err_host = nullptr;                            // mapped pinned: device-side timeout report
     int* err_dev = nullptr;
     unsigned long long p2p_sent[BG_MAX_WORLD][64] = {};
-    cudaEvent_t fused_event = nullptr, fused_barrier_event = nullptr;
-    bool fused_event_valid = false;
     std::mutex mu;
 };
 
@@ -113,8 +111,8 @@ extern "C" int bg_ctx_create(int rank, int world, int device, size_t arena_bytes
         return fail(BG_ENOMEM, "arena cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
     }
     BG_CUDA(cudaMemset(c->arena, 0, pad));
-    BG_CUDA(cudaHostAlloc(&c->err_host, sizeof(int), cudaHostAllocMapped));
-    *c->err_host = 0;
+    BG_CUDA(cudaHostAlloc(&c->err_host, 8 * sizeof(int), cudaHostAllocMapped));   // [0] status, [1..7] who/where
+    for (int i = 0; i < 8; ++i) c->err_host[i] = 0;
     BG_CUDA(cudaHostGetDevicePointer(&c->err_dev, c->err_host, 0));
     BG_CUDA(cudaDeviceSynchronize());
     c->bump = pad;
@@ -194,6 +192,12 @@ extern "C" int bg_arena_attach_local(bg_ctx_t c, int peer, bg_ctx_t other) {
 extern "C" int bg_ctx_error_flag(bg_ctx_t c, int* flag) {
     if (!c || !flag) return fail(BG_EINVAL, "null arg");
     *flag = *c->err_host;
+    return BG_OK;
+}
+
+extern "C" int bg_ctx_error_info(bg_ctx_t c, int* info8) {
+    if (!c || !info8) return fail(BG_EINVAL, "null arg");
+    for (int i = 0; i < 8; ++i) info8[i] = c->err_host[i];   // mapped host memory: readable after a device trap
     return BG_OK;
 }
 
@@ -305,6 +309,10 @@ __device__ __forceinline__ void sig_spin_cas(uint32_t* addr, uint32_t expect, ui
             unsigned long long now = gtimer();
             if (t0 == 0) t0 = now;
             else if (now - t0 > s.timeout_ns) {
+                // who/where: kind 1 = signal a peer (its flag never drained), 2 = wait for a peer's signal
+                if (atomicCAS(s.err + 1, 0, release ? 1 : 2) == 0) {
+                    s.err[2] = (int)blockIdx.x; s.err[3] = (int)threadIdx.x; s.err[4] = (int)old; s.err[5] = s.me; s.err[6] = s.n;
+                }
                 *s.err = BG_ETIMEOUT;
                 __threadfence_system();
                 __trap();
@@ -992,11 +1000,11 @@ extern "C" int bg_p2p_release(bg_ctx_t c, int peer, int flag_id, void* stream) {
 // ------------------------------------------------------------------------------------------------
 int bg_gemm_scatter_launch(const void* a, const void* b, long long m, long long n, long long k, int layout, int p, int me,
                            void* const* partial_ptrs, uint32_t* const* flag_ptrs, void* out, unsigned long long timeout_ns,
-                           int* err_dev, cudaStream_t st_gemm, cudaStream_t st_reduce);
+                           int* err_dev, cudaStream_t st);
 
 extern "C" int bg_gemm_reduce_scatter(bg_ctx_t c, int gid, int lane, const void* a, const void* b, long long m, long long n,
                                       long long k, int layout, const size_t* partial_offs, const size_t* flag_offs, void* out,
-                                      void* stream_gemm, void* stream_reduce) {
+                                      void* stream) {
     Sig s; const Group* g;
     int rc = make_sig(c, gid, lane, &s, &g);
     if (rc) return rc;
@@ -1008,22 +1016,13 @@ extern "C" int bg_gemm_reduce_scatter(bg_ctx_t c, int gid, int lane, const void*
     rc = resolve(c, *g, flag_offs, n_flags * sizeof(uint32_t), &flags);
     if (rc) return rc;
     BG_CUDA(cudaSetDevice(c->device));
-    cudaStream_t sg = (cudaStream_t)stream_gemm, sr = (cudaStream_t)stream_reduce;
-    // the previous fused call's reducer must have drained before peers may overwrite my partial buffer: order my GEMM
-    // stream after it, then meet the peers (every member's GEMM stream passed its own previous reducer)
-    if (c->fused_event_valid) BG_CUDA(cudaStreamWaitEvent(sg, c->fused_event, 0));
-    barrier_kernel<<<1, 32, 0, sg>>>(s);
+    cudaStream_t st = (cudaStream_t)stream;
+    // Entry barrier: every member's previous use of the partial buffers and counters (its last reducer, earlier in this same
+    // stream) has drained before any peer may store into them again.
+    barrier_kernel<<<1, 32, 0, st>>>(s);
     BG_CHECK_LAUNCH();
-    // the reducer must not look at the counters before this barrier either (they may still be mid-reset on a slow rank):
-    if (!c->fused_event_valid) { BG_CUDA(cudaEventCreateWithFlags(&c->fused_event, cudaEventDisableTiming)); BG_CUDA(cudaEventCreateWithFlags(&c->fused_barrier_event, cudaEventDisableTiming)); }
-    BG_CUDA(cudaEventRecord(c->fused_barrier_event, sg));
-    BG_CUDA(cudaStreamWaitEvent(sr, c->fused_barrier_event, 0));
     void* pp[BG_MAX_PEERS]; uint32_t* fp[BG_MAX_PEERS];
     for (int i = 0; i < BG_MAX_PEERS; ++i) { pp[i] = partial.p[i]; fp[i] = (uint32_t*)flags.p[i]; }
-    rc = bg_gemm_scatter_launch(a, b, m, n, k, layout, g->n, g->me, pp, fp, out, (unsigned long long)g_tun.timeout_ms * 1000000ull,
-                                c->err_dev, sg, sr);
-    if (rc) return rc;
-    BG_CUDA(cudaEventRecord(c->fused_event, sr));
-    c->fused_event_valid = true;
-    return BG_OK;
+    return bg_gemm_scatter_launch(a, b, m, n, k, layout, g->n, g->me, pp, fp, out, (unsigned long long)g_tun.timeout_ms * 1000000ull,
+                                  c->err_dev, st);
 }

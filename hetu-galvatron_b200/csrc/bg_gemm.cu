@@ -164,6 +164,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_con
     const int m_blocks = (M + BLOCK_M - 1) / BLOCK_M, n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
     const int num_tiles = m_blocks * n_blocks, k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
 
+    if constexpr (kScatter) {
+        // Programmatic dependent launch: the tile reducer (next kernel in this stream) may be scheduled once EVERY CTA of
+        // this grid is running.  It spins on tiles this grid (and the peers') produce, so it must never take an SM's
+        // registers before the GEMM CTA of that SM is resident.
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -432,7 +438,7 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 }
 
 // One CTA per local tile (grid-strided): wait until all p partial tiles have landed, sum them in fp32, write bf16.
-__global__ void __launch_bounds__(256) tile_reduce_kernel(const __nv_bfloat16* __restrict__ partial, uint32_t* __restrict__ flags,
+__global__ void __launch_bounds__(256, 2) tile_reduce_kernel(const __nv_bfloat16* __restrict__ partial, uint32_t* __restrict__ flags,
                                                           __nv_bfloat16* __restrict__ out, int p, int rows_per_rank, int N,
                                                           int n_blocks, int local_tiles, unsigned long long timeout_ns, int* err) {
     for (int lt = blockIdx.x; lt < local_tiles; lt += gridDim.x) {
@@ -446,7 +452,10 @@ __global__ void __launch_bounds__(256) tile_reduce_kernel(const __nv_bfloat16* _
                 if ((++spins & 0x3ff) == 0) {
                     unsigned long long now = gtimer_ns();
                     if (t0 == 0) t0 = now;
-                    else if (now - t0 > timeout_ns) { *err = BG_ETIMEOUT; __threadfence_system(); __trap(); }
+                    else if (now - t0 > timeout_ns) {
+                        if (atomicCAS(err + 1, 0, 3) == 0) { err[2] = (int)blockIdx.x; err[3] = lt; err[4] = (int)v; err[5] = p; err[6] = local_tiles; }
+                        *err = BG_ETIMEOUT; __threadfence_system(); __trap();
+                    }
                 }
             }
         }
@@ -483,9 +492,11 @@ __global__ void __launch_bounds__(256) tile_reduce_kernel(const __nv_bfloat16* _
 }  // namespace
 
 // Internal entry used by bg_comm.cu (which owns contexts, groups and peer pointers).  partial/flags: per-member pointers.
+// Both kernels go to ONE stream: the GEMM, then the reducer as its programmatic dependent (it starts when all GEMM CTAs are
+// resident, not when they finish, and never calls griddepcontrol.wait -- tiles are handed over through the arrival counters).
 int bg_gemm_scatter_launch(const void* a, const void* b, long long m, long long n, long long k, int layout, int p, int me,
                            void* const* partial_ptrs, uint32_t* const* flag_ptrs, void* out, unsigned long long timeout_ns,
-                           int* err_dev, cudaStream_t st_gemm, cudaStream_t st_reduce) {
+                           int* err_dev, cudaStream_t st) {
     if (layout < 0 || layout > 2) return fail(BG_EINVAL, "bg_gemm_reduce_scatter: layout %d", layout);
     if (m <= 0 || n <= 0 || k <= 0 || n % 8 || k % 8) return fail(BG_EINVAL, "bg_gemm_reduce_scatter: bad dims");
     if (m % ((long long)p * BLOCK_M)) return fail(BG_EINVAL, "bg_gemm_reduce_scatter: M=%lld must be a multiple of p*%d", m, BLOCK_M);
@@ -521,15 +532,21 @@ int bg_gemm_scatter_launch(const void* a, const void* b, long long m, long long 
     const long long tiles = (long long)m_blocks * n_blocks;
     const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
     const int local_tiles = (rows_per_rank / BLOCK_M) * n_blocks;
-    // reducer first (it only waits on flags), so it is resident when the first tiles land
-    int rgrid = local_tiles < 2 * g_num_sms ? local_tiles : 2 * g_num_sms;   // co-resident with the GEMM CTAs (256 thr, no smem)
-    tile_reduce_kernel<<<rgrid, 256, 0, st_reduce>>>((const __nv_bfloat16*)partial_ptrs[me], flag_ptrs[me], (__nv_bfloat16*)out, p,
-                                                     rows_per_rank, (int)n, n_blocks, local_tiles, timeout_ns, err_dev);
-    BG_CHECK_LAUNCH();
     const CUtensorMap& mc_unused = sp.dst[0];
-    if (layout == kTN) gemm_bf16_kernel<kTN, true><<<grid, kThreads, kSmemBytes, st_gemm>>>(ma, mb, mc_unused, nullptr, (int)m, (int)n, (int)k, 0, sp);
-    else if (layout == kNN) gemm_bf16_kernel<kNN, true><<<grid, kThreads, kSmemBytes, st_gemm>>>(ma, mb, mc_unused, nullptr, (int)m, (int)n, (int)k, 0, sp);
-    else gemm_bf16_kernel<kNT, true><<<grid, kThreads, kSmemBytes, st_gemm>>>(ma, mb, mc_unused, nullptr, (int)m, (int)n, (int)k, 0, sp);
+    if (layout == kTN) gemm_bf16_kernel<kTN, true><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc_unused, nullptr, (int)m, (int)n, (int)k, 0, sp);
+    else if (layout == kNN) gemm_bf16_kernel<kNN, true><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc_unused, nullptr, (int)m, (int)n, (int)k, 0, sp);
+    else gemm_bf16_kernel<kNT, true><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc_unused, nullptr, (int)m, (int)n, (int)k, 0, sp);
     BG_CHECK_LAUNCH();
+    // one reducer CTA fits beside a GEMM CTA (registers); more CTAs than SMs only queue
+    const int rgrid = local_tiles < g_num_sms ? local_tiles : g_num_sms;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)rgrid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    BG_CUDA(cudaLaunchKernelEx(&cfg, tile_reduce_kernel, (const __nv_bfloat16*)partial_ptrs[me], (uint32_t*)flag_ptrs[me],
+                               (__nv_bfloat16*)out, p, rows_per_rank, (int)n, n_blocks, local_tiles, timeout_ns, err_dev));
+    bg::g_launches.fetch_add(1, std::memory_order_relaxed);
     return BG_OK;
 }

@@ -33,20 +33,39 @@ def estimate_arena_bytes(config, args, hp_configs):
         + 3 * f * h + 2 * h
     pp = hp_configs["pp_deg"]
     esz = 4 if args.mixed_precision == "fp32" else 2
-    total = 0
+    gsz = 4 if getattr(args, "reduce_in_fp32", False) else esz
+    world = _world.get_world_size()
+    slots = int(getattr(args, "zero3_pool_slots", 0))
+    chunks = args.chunks if args.chunks > 0 else 1
+    pool_grads = chunks == 1 or not args.async_grad_reduce
+    vocab = V * h // max(1, args.vocab_tp)
+    embed_zero3 = bool(getattr(args, "embed_sdp", 0)) or args.default_dp_type == "zero3"
     worst_stage = 0
     for stage in range(pp):
-        n = 0
-        for tp, rank in zip(hp_configs["tp_sizes_enc"], hp_configs["pp_ranks_enc"]):
-            if rank == stage:
-                n += layer // tp if not False else layer
+        fixed_w = fixed_g = 0           # layers that keep their own buffers
+        pooled = 0                      # largest pooled layer of the stage
+        # Ulysses layers keep whole parameters (tp_sizes_enc is then the sequence-parallel degree) and shard them over
+        # the DP x SP x CP group (comm_groups.py:475-483)
+        use_sp = hp_configs.get("use_sp") or [0] * len(hp_configs["tp_sizes_enc"])
+        rows = [(layer if sp else layer // tp, (dt == 1 or args.default_dp_type == "zero3"), 1 if sp else tp * max(1, cp))
+                for tp, cp, dt, rank, sp in zip(hp_configs["tp_sizes_enc"], hp_configs["cp_sizes_enc"], hp_configs["dp_types_enc"],
+                                                hp_configs["pp_ranks_enc"], use_sp) if rank == stage]
         if stage == 0:
-            n += V * h // max(1, args.vocab_tp)
+            rows.append((vocab, embed_zero3, max(1, args.vocab_tp)))
         if stage == pp - 1:
-            n += V * h // max(1, args.vocab_tp) + h
-        worst_stage = max(worst_stage, n)
-    total = worst_stage * esz * 2
-    world = _world.get_world_size()
+            rows.append((vocab, embed_zero3, max(1, args.vocab_tp)))
+            rows.append((h, embed_zero3, max(1, args.vocab_tp)))
+        for n, zero3, model_par in rows:
+            sharded = world // pp // model_par > 1
+            if zero3 and sharded and slots > 0:
+                pooled = max(pooled, n)
+                fixed_g += 0 if pool_grads else n
+            else:
+                fixed_w += n
+                fixed_g += n
+        total_stage = fixed_w * esz + fixed_g * gsz + pooled * (slots * esz + (max(2, slots - 1) * gsz if pool_grads else 0))
+        worst_stage = max(worst_stage, total_stage)
+    total = worst_stage
     min_dp = max(1, world // pp // max(max(hp_configs["tp_sizes_enc"]), args.vocab_tp) // max(hp_configs["cp_sizes_enc"]))
     mbs = -(-args.global_train_batch_size // min_dp // max(1, args.chunks if args.chunks > 0 else 1))
     act = int(config.max_position_embeddings * mbs * h * esz * 1.5) + (1 << 20)

@@ -59,6 +59,11 @@ int bg_arena_export(bg_ctx_t ctx, void* handle64);                      /* cudaI
 int bg_arena_import(bg_ctx_t ctx, int peer_rank, const void* handle64); /* map a peer process's arena */
 int bg_arena_attach_local(bg_ctx_t ctx, int peer_rank, bg_ctx_t peer);  /* peer ctx in this process */
 int bg_ctx_error_flag(bg_ctx_t ctx, int* flag);                         /* device-side timeout report */
+/* info8[0] = status; [1] = kind (1 signalling a peer, 2 waiting for a peer, 3 fused-GEMM tile reducer);
+ * [2] = CTA; [3] = thread or tile; [4] = value last seen; [5], [6] = group index/size or expected count/tiles.
+ * The reference's analogue is the NCCL watchdog's timeout dump (ProcessGroupNCCL); here a lost peer traps the
+ * kernel and leaves this record in mapped host memory. */
+int bg_ctx_error_info(bg_ctx_t ctx, int* info8);
 
 /* ---- groups (galvatron/core/runtime/comm_groups.py:7-29 CommGroup / :416 gen_comm_groups) ---------------- */
 /* A group is its rank list; creation is O(1), local, and needs no collective (the reference pays one
@@ -162,13 +167,13 @@ int bg_gemm_bf16(const void* a, const void* b, void* c, long long m, long long n
 
 /* C5/C8 fused with K1: C = A op B is computed in 128x256 tcgen05 tiles and REDUCE-SCATTERED along M over the group inside
  * the same operation -- every finished partial tile is TMA-stored into the owning rank's arena (peer HBM over NVLink) and
- * counted there; a tile reducer on the owner (stream_reduce) sums the p partials as they land and writes out[M/p, N].
+ * counted there; a tile reducer on the owner -- launched into the same stream as the GEMM's programmatic dependent, so it
+ * runs beside the GEMM CTAs once all of them are resident -- sums the p partials as they land and writes out[M/p, N].
  * Replaces layers.py:1061-1109 (row-parallel GEMM then mappings_group.py:120 reduce-scatter) and :462,488-494 (dgrad +
  * reduce-scatter).  partial_offs: symmetric bf16 buffer of M*N elements; flag_offs: symmetric u32[(M/p/128)*ceil(N/256)],
- * zero-initialised.  M must be a multiple of p*128.  The consumer of `out` must wait for stream_reduce. */
+ * zero-initialised.  M must be a multiple of p*128.  `out` is complete in stream order. */
 int bg_gemm_reduce_scatter(bg_ctx_t ctx, int gid, int lane, const void* a, const void* b, long long m, long long n, long long k,
-                           int layout, const size_t* partial_offs, const size_t* flag_offs, void* out, void* stream_gemm,
-                           void* stream_reduce);
+                           int layout, const size_t* partial_offs, const size_t* flag_offs, void* out, void* stream);
 
 #ifdef __cplusplus
 }

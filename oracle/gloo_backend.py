@@ -100,6 +100,15 @@ class OracleBackend:
     def finish_reductions(self):
         pass
 
+    def record_event(self):
+        return None
+
+    def reduce_done_event(self):
+        return None
+
+    def wait_event(self, ev):
+        pass
+
     def unit_unshard(self, unit):
         shard = unit.flat_param.data.to(unit.param_dtype)
         if unit.dp_type == "ddp" or unit.group.size == 1:

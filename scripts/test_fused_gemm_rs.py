@@ -51,10 +51,21 @@ def main():
         a = (torch.randn(M, K, device="cuda") * 0.5).to(BF)
         b = (torch.randn((N, K) if layout == "tn" else (K, N), device="cuda") * 0.5).to(BF)
         out = be.gemm_reduce_scatter(a, b, layout, grp)
+        if os.environ.get("HGB_DIAG"):   # snapshot of the arrival counters while the kernels may still be spinning
+            import time
+            time.sleep(3)
+            side = torch.cuda.Stream()
+            buf = be.staging(grp, M * N * 2)
+            n_flags = (M // world // 128) * ((N + 255) // 256)
+            with torch.cuda.stream(side):
+                cnt = buf.u8[buf.data_bytes: buf.data_bytes + n_flags * 4].view(torch.int32).to("cpu", non_blocking=False)
+            hist = {int(v): int((cnt == v).sum()) for v in cnt.unique()}
+            print("rank %d: %s K=%d arrival counters %s, compute stream done=%s" % (
+                rank, layout, K, hist, torch.cuda.current_stream().query()), file=sys.stderr, flush=True)
         try:
             torch.cuda.synchronize()
         except RuntimeError as exc:
-            print("rank %d: fused GEMM+RS failed (%s), error flag %s" % (rank, str(exc).splitlines()[0], be.comm.error_flag()), file=sys.stderr, flush=True)
+            print("rank %d: fused GEMM+RS failed (%s), error info %s" % (rank, str(exc).splitlines()[0], be.comm.error_info()), file=sys.stderr, flush=True)
             raise
         full = torch.matmul(a, b.t() if layout == "tn" else b)
         ref = torch.empty(M // world, N, device="cuda", dtype=BF)
@@ -63,7 +74,11 @@ def main():
         err = float((out.float() - ref.float()).abs().max() / (ref.float().abs().max() + 1e-6))
         for _ in range(3):   # repeated use: counters must reset, buffers must be reusable
             out2 = be.gemm_reduce_scatter(a, b, layout, grp)
-        torch.cuda.synchronize()
+        try:
+            torch.cuda.synchronize()
+        except RuntimeError:
+            print("rank %d: repeated fused GEMM+RS failed, error info %s" % (rank, be.comm.error_info()), file=sys.stderr, flush=True)
+            raise
         same = bool(torch.equal(out.view(torch.int16), out2.view(torch.int16)))
         fused_ms = timed(lambda: be.gemm_reduce_scatter(a, b, layout, grp))
 

@@ -106,7 +106,7 @@ def main():
     args = sm.tiny_args(**over)
     config, model = sm.build(args, dict(sm.TINY, **spec) if spec else None)
     opt, _ = get_optimizer_and_param_scheduler(model, args)
-    w = assemble_full(model, config, world, rank, lambda u: u.w_flat)
+    w = assemble_full(model, config, world, rank, lambda u: u.read_full_params())
     w = {k: (v.cpu().clone() if torch.is_tensor(v) else [{kk: vv.cpu().clone() for kk, vv in lw.items()} for lw in v]) for k, v in w.items()}
 
     gbs, seq = args.global_train_batch_size, config.max_position_embeddings
@@ -160,8 +160,15 @@ def main():
                       "n_reduce": [u.n_reduce for u in model.model.units]}
             assert abs(mean_loss - float(ref_loss)) <= 5e-3 * abs(float(ref_loss)), report
             assert report["max_grad_err"] < tol, (report, errs)
+        else:
+            lt = torch.tensor([loss if loss is not None else 0.0, 1.0 if loss is not None else 0.0], dtype=torch.float64, device=dev)
+            dist.all_reduce(lt)
+            report["loss_step1"] = float(lt[0] / lt[1])       # after one optimizer update: re-gathered parameters
         opt.step()
         opt.zero_grad()
+    report["n_unshard_2steps"] = [u.n_unshard for u in model.model.units]
+    report["pools"] = {"%s:%s" % (k[2], "-".join(map(str, k[0]))): [p.n_slots, p.n_gather_skipped, len(p.held)]
+                       for k, p in getattr(be, "_zero3_pools", {}).items()}
     if use_cuda:
         report["launches"] = be.launch_count()
     if rank == 0:

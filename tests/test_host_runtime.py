@@ -40,6 +40,9 @@ WORLD2 = {
     "dp2_zero2": dict(default_dp_type="zero2"),
     "dp2_zero3_ckpt_chunks2": dict(sdp=1, global_checkpoint=1, chunks=2),
     "dp2_ddp_chunks2": dict(default_dp_type="ddp", chunks=2),
+    "dp2_zero3_nopool": dict(sdp=1, embed_sdp=1, zero3_pool_slots=0),
+    "dp2_zero3_pool2": dict(sdp=1, embed_sdp=1, zero3_pool_slots=2),
+    "dp2_zero3_pool2_no_async_chunks2": dict(sdp=1, embed_sdp=1, zero3_pool_slots=2, chunks=2, async_grad_reduce=False),
     "dp2_zero2_no_async_chunks2": dict(default_dp_type="zero2", chunks=2, async_grad_reduce=False),
     "tp2": dict(global_tp_deg=2, vocab_tp=2),
     "tp2_megatron_sp": dict(global_tp_deg=2, vocab_tp=2, sequence_parallel=True),
@@ -84,6 +87,16 @@ def test_world2(name):
         assert set(rep["n_unshard"]) <= {0, 1} and set(rep["n_reduce"]) == {1}
     if name == "dp2_zero2_no_async_chunks2":
         assert set(rep["n_reduce"]) == {2}     # --no_async_grad_reduce: every microbatch is reduced
+    if name.startswith("dp2_zero3_pool2"):
+        # two rotating buffers serve every layer: parameters are re-gathered for backward (FULL_SHARD), gradients share a
+        # pool too, nothing stays held after the step -- and the numbers are those of the one-buffer-per-layer layout
+        assert set(rep["pools"]) == {"param:0-1", "grad:0-1"} and all(v[0] == 2 and v[2] == 0 for v in rep["pools"].values())
+        assert max(rep["n_unshard_2steps"]) >= 2 * 2
+        base = launch(2, dict(WORLD2["dp2_zero3_nopool" if "chunks2" not in name else "dp2_zero3_nopool"], **(
+            {} if "chunks2" not in name else dict(chunks=2, async_grad_reduce=False))))
+        assert rep["loss"] == base["loss"] and rep["loss_step1"] == base["loss_step1"]
+    if name == "dp2_zero3_nopool":
+        assert rep["pools"] == {}
 
 
 @pytest.mark.parametrize("name", sorted(WORLD4))
