@@ -121,12 +121,14 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
 }
 
 struct TileCoord { int m, n; };
-__device__ __forceinline__ TileCoord tile_of(int t, int m_blocks, int n_blocks) {
+__device__ __forceinline__ TileCoord tile_of(int t, int m_blocks, int n_blocks, int m_rot = 0) {
     const int per_group = kGroupM * n_blocks;
     const int g = t / per_group, first_m = g * kGroupM;
     const int rows = min(kGroupM, m_blocks - first_m);
     const int r = t - g * per_group;
-    return {first_m + r % rows, r / rows};
+    int m = first_m + r % rows + m_rot;     // m_rot: fused scatter starts every rank on a different owner's rows
+    if (m >= m_blocks) m -= m_blocks;
+    return {m, r / rows};
 }
 
 // Fused GEMM + reduce-scatter (C5/C8): instead of storing C locally, the epilogue TMA-stores every finished 128x256 partial
@@ -164,6 +166,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_con
     const int m_blocks = (M + BLOCK_M - 1) / BLOCK_M, n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
     const int num_tiles = m_blocks * n_blocks, k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
 
+    // Fused scatter: rank r walks the owners in the order r+1, r+2, ..., r (ring schedule), so at any moment every owner
+    // receives from ONE peer instead of all p-1 at once (incast would serialise the job on one GPU's NVLink ingress), and
+    // the rank's own rows -- which need no NVLink -- come last, when the links are draining.
+    int m_rot = 0;
+    if constexpr (kScatter) m_rot = ((sp.me + 1) % sp.p) * (sp.rows_per_rank / BLOCK_M);
     if constexpr (kScatter) {
         // Programmatic dependent launch: the tile reducer (next kernel in this stream) may be scheduled once EVERY CTA of
         // this grid is running.  It spins on tiles this grid (and the peers') produce, so it must never take an SM's
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_con
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const TileCoord tc = tile_of(t, m_blocks, n_blocks);
+                const TileCoord tc = tile_of(t, m_blocks, n_blocks, m_rot);
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
                     const uint32_t bar = smem_u32(full_bar + stage);
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_con
         int buf = 0;
         uint32_t* prev_flag = nullptr;                // fused scatter: arrival counter of the tile whose stores are in flight
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            const TileCoord tc = tile_of(t, m_blocks, n_blocks);
+            const TileCoord tc = tile_of(t, m_blocks, n_blocks, m_rot);
             mbar_wait(smem_u32(tmem_full + acc), acc_phase);
             tc_fence_after();
 #pragma unroll 1
