@@ -352,4 +352,13 @@ if __name__ == "__main__":
     if o.impl == "reference":
         run_reference(o)
     else:
-        run_ours(o)
+        try:
+            run_ours(o)
+        except Exception:
+            # a device-side barrier timeout traps the kernel; its who/where record survives in mapped host memory
+            try:
+                from hetu_galvatron_b200.core.runtime.backend import get_backend
+                sys.stderr.write("rank %s: device error info %s\n" % (os.environ.get("RANK", "0"), get_backend().comm.error_info()))
+            except Exception:
+                pass
+            raise

@@ -4,6 +4,7 @@ There is no CPU path: if ``libbg_galvatron.so`` is missing or fails to load, eve
 plumbing here (device memory, streams, the bootstrap exchange of IPC handles); the collectives themselves
 are the hand-written sm_100a kernels in ``csrc/``.
 """
+import contextlib
 import ctypes
 import os
 import threading
@@ -181,6 +182,7 @@ class BgComm:
     def __init__(self, rank, world, device, arena_bytes):
         import torch
         self.rank, self.world, self.device = int(rank), int(world), int(device)
+        self._last_coll, self._coll_events, self._coll_i = None, None, 0
         self._ctx = _vp()
         torch.cuda.set_device(self.device)
         torch.cuda.init()
@@ -280,8 +282,30 @@ class BgComm:
         self._pending = []
 
     # ---- collectives (async on the current or given torch stream) -------------------------------------
+    @contextlib.contextmanager
+    def _in_order(self, stream):
+        """Every kernel that waits on peers is launched in ONE total order per rank, whatever stream it is on: it first waits
+        (event) for the previous such kernel when that one went to another stream.  Two peer-waiting kernels running side by
+        side can each hold the registers the other needs on a different rank (A runs X and cannot place Y, B runs Y and
+        cannot place X) -- a cross-rank deadlock seen with ZeRO-3's concurrent all-gather and reduce-scatter at Llama-70B
+        sizes.  The program order is the same on every rank, so a single chain per rank is deadlock-free; kernels that do
+        not wait on peers (GEMMs, attention, elementwise) still overlap freely with the chain."""
+        import torch
+        s = torch.cuda.current_stream() if stream is None else stream
+        last = self._last_coll
+        if last is not None and last[0] != s.cuda_stream:
+            s.wait_event(last[1])
+        yield _vp(s.cuda_stream)
+        if self._coll_events is None:
+            self._coll_events = [torch.cuda.Event() for _ in range(8)]
+        ev = self._coll_events[self._coll_i % 8]
+        self._coll_i += 1
+        ev.record(s)
+        self._last_coll = (s.cuda_stream, ev)
+
     def barrier(self, group, lane=LANE_MISC, stream=None):
-        check(lib().bg_barrier(self._ctx, self.group_id(group), lane, _stream_ptr(stream)))
+        with self._in_order(stream) as sp:
+            check(lib().bg_barrier(self._ctx, self.group_id(group), lane, sp))
 
     def all_gather_cast(self, group, src, dst, shard_elems=None, lane=LANE_UNSHARD, stream=None, dst_dtype=None,
                         dst_byte_offset=0):
@@ -290,30 +314,34 @@ class BgComm:
         n = src.numel() if shard_elems is None else int(shard_elems)
         dd = torch.bfloat16 if dst_dtype is None else dst_dtype
         offs = dst.offs() if dst_byte_offset == 0 else dst.sub(dst_byte_offset)
-        check(lib().bg_all_gather_cast(self._ctx, self.group_id(group), lane, _ptr(src), dtype_code(src.dtype), offs,
-                                       dtype_code(dd), n, _stream_ptr(stream)))
+        with self._in_order(stream) as sp:
+            check(lib().bg_all_gather_cast(self._ctx, self.group_id(group), lane, _ptr(src), dtype_code(src.dtype), offs,
+                                           dtype_code(dd), n, sp))
 
     def reduce_scatter_acc(self, group, src, src_dtype, dst, shard_elems=None, prescale=1.0, postscale=1.0,
                            accumulate=False, lane=LANE_REDUCE, stream=None, src_byte_offset=0):
         """dst[shard] = [dst +] sum_members(src_member[my slice]) * prescale * postscale."""
         n = dst.numel() if shard_elems is None else int(shard_elems)
         offs = src.offs() if src_byte_offset == 0 else src.sub(src_byte_offset)
-        check(lib().bg_reduce_scatter_acc(self._ctx, self.group_id(group), lane, offs, dtype_code(src_dtype), _ptr(dst),
-                                          dtype_code(dst.dtype), n, float(prescale), float(postscale),
-                                          1 if accumulate else 0, _stream_ptr(stream)))
+        with self._in_order(stream) as sp:
+            check(lib().bg_reduce_scatter_acc(self._ctx, self.group_id(group), lane, offs, dtype_code(src_dtype), _ptr(dst),
+                                              dtype_code(dst.dtype), n, float(prescale), float(postscale),
+                                              1 if accumulate else 0, sp))
 
     def reduce_scatter_adamw(self, group, src, src_dtype, param, exp_avg, exp_avg_sq, shard_elems, prescale, postscale, lr, beta1,
                              beta2, eps, weight_decay, step, lane=LANE_REDUCE, stream=None):
-        check(lib().bg_reduce_scatter_adamw(self._ctx, self.group_id(group), lane, src.offs(), dtype_code(src_dtype), _ptr(param),
-                                            _ptr(exp_avg), _ptr(exp_avg_sq), int(shard_elems), float(prescale), float(postscale),
-                                            float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
-                                            _stream_ptr(stream)))
+        with self._in_order(stream) as sp:
+            check(lib().bg_reduce_scatter_adamw(self._ctx, self.group_id(group), lane, src.offs(), dtype_code(src_dtype), _ptr(param),
+                                                _ptr(exp_avg), _ptr(exp_avg_sq), int(shard_elems), float(prescale), float(postscale),
+                                                float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+                                                sp))
 
     def all_reduce(self, group, src, dst, elems=None, op=SUM, scale=1.0, lane=LANE_ACT, stream=None, src_byte_offset=0):
         n = dst.numel() if elems is None else int(elems)
         offs = src.offs() if src_byte_offset == 0 else src.sub(src_byte_offset)
-        check(lib().bg_all_reduce(self._ctx, self.group_id(group), lane, offs, _ptr(dst), n, dtype_code(dst.dtype), op,
-                                  float(scale), _stream_ptr(stream)))
+        with self._in_order(stream) as sp:
+            check(lib().bg_all_reduce(self._ctx, self.group_id(group), lane, offs, _ptr(dst), n, dtype_code(dst.dtype), op,
+                                      float(scale), sp))
 
     def all_to_all_rows(self, group, descs, dtype, lane=LANE_ACT, stream=None):
         """descs: list of dicts with keys src(SymBuffer) [src_byte_offset] dst(tensor) batch rows row_elems src_bs src_rs
@@ -327,15 +355,17 @@ class BgComm:
             arr[i].dst = d["dst"].data_ptr()
             for k in ("batch", "rows", "row_elems", "src_bs", "src_rs", "src_me_off", "dst_bs", "dst_rs", "dst_peer_off"):
                 setattr(arr[i], k, int(d[k]))
-        check(lib().bg_all_to_all_rows(self._ctx, self.group_id(group), lane, arr, len(descs), dtype_code(dtype),
-                                       _stream_ptr(stream)))
+        with self._in_order(stream) as sp:
+            check(lib().bg_all_to_all_rows(self._ctx, self.group_id(group), lane, arr, len(descs), dtype_code(dtype),
+                                           sp))
 
     def gemm_reduce_scatter(self, group, a, b, m, n, k, layout, partial, partial_byte_offset, flags_byte_offset, out,
                             lane=LANE_ACT, stream=None):
         """C = A op B reduce-scattered along M over ``group`` in one fused operation (partial tiles -> owner's HBM)."""
-        check(lib().bg_gemm_reduce_scatter(self._ctx, self.group_id(group), lane, _ptr(a), _ptr(b), int(m), int(n), int(k), int(layout),
-                                           partial.sub(partial_byte_offset), partial.sub(flags_byte_offset), _ptr(out),
-                                           _stream_ptr(stream)))
+        with self._in_order(stream) as sp:
+            check(lib().bg_gemm_reduce_scatter(self._ctx, self.group_id(group), lane, _ptr(a), _ptr(b), int(m), int(n), int(k), int(layout),
+                                               partial.sub(partial_byte_offset), partial.sub(flags_byte_offset), _ptr(out),
+                                               sp))
 
     def p2p_send(self, peer_rank, dst_offset, src, flag_id, stream=None):
         check(lib().bg_p2p_send(self._ctx, int(peer_rank), int(dst_offset), _ptr(src), src.numel() * src.element_size(),

@@ -36,7 +36,9 @@ DEFAULTS = dict(
     reduce_in_fp32=False,                # :187
     entropy_in_fp32=False,               # :192
     distributed_checkpoint=False,        # :197
-    load=None,
+    load=None,                           # megatron --load: checkpoint directory (HF-layered, or distributed with the flag above)
+    load_iteration=0,                    # :204
+    save=None,                           # megatron --save: reserves the peer-visible gather buffer checkpoint export needs
     lr=1e-4,                             # :209
     local_rank=0,                        # :211
     # megatron-side flags the layer code reads

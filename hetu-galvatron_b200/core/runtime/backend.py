@@ -68,6 +68,8 @@ class CudaBackend:
             if self.world > 1:
                 comm.connect_ipc()
         self.comm = comm
+        if os.environ.get("HGB_TIMEOUT_MS"):      # device-side barrier timeout (default 60 s): shorter for debugging runs
+            _bg.set_tunable("timeout_ms", int(os.environ["HGB_TIMEOUT_MS"]))
         self.unshard_stream = torch.cuda.Stream(device=self.device)
         self.reduce_stream = torch.cuda.Stream(device=self.device)
         self.p2p_stream = torch.cuda.Stream(device=self.device)
@@ -191,6 +193,36 @@ class CudaBackend:
 
     def finish_reductions(self):
         torch.cuda.current_stream().wait_stream(self.reduce_stream)
+
+    # ---- checkpoint export: gather the fp32 master shards of one unit (C1 with an fp32 destination) -----------------------
+    def reserve_checkpoint_gather(self, group, nbytes):
+        """Peer-visible landing buffer for ``gather_master`` (one per group, sized for its largest unit); before ``exchange()``."""
+        if group is None or group.size == 1:
+            return
+        bufs = self.__dict__.setdefault("_ckpt_bufs", {})
+        key = tuple(group.ranks)
+        cur = bufs.get(key)
+        if cur is None or cur.nbytes < nbytes:
+            if cur is not None and cur.offsets is not None:
+                raise self.bg.BgError("checkpoint gather buffer for group %s is already exchanged" % (key,))
+            bufs[key] = self.comm.sym_alloc(group, int(nbytes))
+
+    def gather_master(self, unit):
+        """Full fp32 flat parameter of ``unit`` on every member of its group (collective)."""
+        if unit.dp_type == "ddp" or unit.group.size == 1:
+            return unit.flat_param.data
+        buf = self.__dict__.get("_ckpt_bufs", {}).get(tuple(unit.group.ranks))
+        if buf is None or buf.nbytes < unit.padded * 4:
+            raise self.bg.BgError("no checkpoint gather buffer reserved for group %s: construct the model with args.save set" % (unit.group.ranks,))
+        self.comm.all_gather_cast(unit.group, unit.flat_param.data, buf, shard_elems=unit.shard_elems, lane=self.bg.LANE_MISC,
+                                  dst_dtype=torch.float32)
+        return buf.view(torch.float32, unit.padded).clone()
+
+    def barrier_all(self):
+        torch.cuda.synchronize()
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()
 
     # ---- events (ordering between successive occupants of a pooled zero3 buffer) ------------------------------------------
     def record_event(self):

@@ -112,6 +112,15 @@ def construct_hybrid_parallel_model_api(model, model_config, training_args, hybr
     hp_whole = hp_config_whole_model(module_types, hp_configs, embed_sdp=args.embed_sdp, embed_ckpt=0, vocab_tp=args.vocab_tp,
                                      vocab_sp=args.vocab_sp, vocab_cp=getattr(args, "vocab_cp", 1))
 
+    # Ulysses rows keep the sequence split across their group; every other row does so only under Megatron sequence
+    # parallelism.  The relocation between the two layouts is keyed on --sequence-parallel (redistribute.py:60,121,282,335), so
+    # without it a strategy that mixes them is silently wrong in the reference (its own hybrid tests set the flag,
+    # tests/core/test_hybrid.py:45).  Refuse it.
+    sp_rows = [s > 1 for s in hp_whole["sp_sizes_whole"]]
+    if any(sp_rows) and not all(sp_rows) and not args.sequence_parallel:
+        raise ValueError("this strategy mixes Ulysses layers (use_sp=1) with tensor-parallel / data-parallel rows: "
+                         "it needs --sequence-parallel (activations must be sequence-split on both sides of a relocation)")
+
     # [Step 0] communication groups (pure rank lists)
     (pp_group, tp_groups_whole, sp_groups_whole, cp_groups_whole, dp_groups_whole, seq_data_groups_whole,
      allgather_tp_sp_groups_whole, split_tp_sp_groups_whole, allgather_cp_groups_whole, split_cp_groups_whole,

@@ -100,6 +100,20 @@ class OracleBackend:
     def finish_reductions(self):
         pass
 
+    def reserve_checkpoint_gather(self, group, nbytes):
+        pass
+
+    def gather_master(self, unit):
+        if unit.dp_type == "ddp" or unit.group.size == 1:
+            return unit.flat_param.data
+        full = torch.empty(unit.padded, dtype=torch.float32)
+        dist.all_gather_into_tensor(full, unit.flat_param.data.contiguous(), group=self._pg(unit.group))
+        return full
+
+    def barrier_all(self):
+        if dist.is_initialized():
+            dist.barrier()
+
     def record_event(self):
         return None
 

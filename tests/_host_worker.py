@@ -158,6 +158,15 @@ def main():
             report = {"loss": mean_loss, "ref_loss": float(ref_loss), "max_grad_err": max(errs.values()),
                       "worst": max(errs, key=errs.get), "n_unshard": [u.n_unshard for u in model.model.units],
                       "n_reduce": [u.n_reduce for u in model.model.units]}
+            if os.environ.get("HOST_TEST_DEBUG") and rank == 0:
+                def fit(a, b):
+                    a, b = a.float().reshape(-1), b.float().reshape(-1)
+                    return "ratio %.4f cos %.5f" % (float(a @ b / (b @ b + 1e-30)), float(a @ b / (a.norm() * b.norm() + 1e-30)))
+                print("DEBUG embed", fit(got["embed"], w["embed"].grad), "scale", scale["embed_0"], flush=True)
+                print("DEBUG lm_head", fit(got["lm_head"], w["lm_head"].grad), flush=True)
+                print("DEBUG norm", fit(got["norm"], w["norm"].grad), flush=True)
+                for i, (gl, wl) in enumerate(zip(got["layers"], w["layers"])):
+                    print("DEBUG layer", i, "scale", scale["gpt_dec_%d" % (i + 1)], {k: fit(gl[k], wl[k].grad) for k in gl}, flush=True)
             assert abs(mean_loss - float(ref_loss)) <= 5e-3 * abs(float(ref_loss)), report
             assert report["max_grad_err"] < tol, (report, errs)
         else:

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from test_host_runtime import WORLD1, WORLD2, WORLD4, launch  # noqa: E402
+from test_host_runtime import WORLD1, WORLD2, WORLD4, WORLD8, launch  # noqa: E402
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
@@ -37,6 +37,14 @@ def test_two_gpus(name):
 def test_four_gpus(name):
     _need(4)
     rep = launch(4, dict(WORLD4[name]), backend="cuda")
+    assert rep["max_grad_err"] < 3e-2 and rep["launches"] > 0
+
+
+@pytest.mark.parametrize("name", sorted(WORLD8))
+def test_eight_gpus(name):
+    """The reference's own 8-GPU hybrid corpus (tests/core/test_hybrid.py:122-183) on the product path."""
+    _need(8)
+    rep = launch(8, dict(WORLD8[name]), backend="cuda", timeout=900)
     assert rep["max_grad_err"] < 3e-2 and rep["launches"] > 0
 
 

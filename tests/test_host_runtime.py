@@ -72,6 +72,25 @@ WORLD4 = {
 }
 
 
+# The reference's own 8-GPU hybrid corpus, verbatim (tests/core/test_hybrid.py:122-183): per-layer tp 1/2/4/8 with Megatron-TP
+# and Ulysses layers alternating, ZeRO-2/ZeRO-3 alternating, checkpointing on the last two layers, relocation between every
+# pair of layers, with and without pipeline parallelism, vocab tp 2 or Ulysses-sp 4; Megatron sequence parallelism on, as the
+# reference test sets it (test_hybrid.py:45).
+_HYBRID = dict(tp_consecutive_flags="1,1,1,1", use_sp="0,1,0,1", checkpoint="0,0,1,1", global_bsz=32,
+               pipeline_type="pipedream_flush", default_dp_type="zero2")
+_SPEC8 = {"n_heads": 8, "n_kv_heads": 8, "n_layers": 4}
+WORLD8 = {
+    "ref_hybrid0_pp1_vtp2": dict(_spec=_SPEC8, sequence_parallel=True, _strategy_json=dict(_HYBRID, pp_deg=1, tp_sizes_enc="1,2,4,8", dp_types_enc="0,1,0,1",
+                                                                  chunks=2, pp_division="4", vtp=2, vsp=0)),
+    "ref_hybrid1_pp1_vsp4": dict(_spec=_SPEC8, sequence_parallel=True, _strategy_json=dict(_HYBRID, pp_deg=1, tp_sizes_enc="1,2,4,8", dp_types_enc="1,0,1,0",
+                                                                  chunks=2, pp_division="4", vtp=4, vsp=1)),
+    "ref_hybrid2_pp2_vtp2": dict(_spec=_SPEC8, sequence_parallel=True, _strategy_json=dict(_HYBRID, pp_deg=2, tp_sizes_enc="1,2,4,2", dp_types_enc="0,1,0,1",
+                                                                  chunks=2, pp_division="3,1", vtp=2, vsp=0)),
+    "ref_hybrid3_pp2_vsp4": dict(_spec=_SPEC8, sequence_parallel=True, _strategy_json=dict(_HYBRID, pp_deg=2, tp_sizes_enc="1,2,4,2", dp_types_enc="1,0,1,0",
+                                                                  chunks=4, pp_division="2,2", vtp=4, vsp=1)),
+}
+
+
 @pytest.mark.parametrize("name", sorted(WORLD1))
 def test_world1(name):
     rep = launch(1, dict(WORLD1[name]))
@@ -102,4 +121,10 @@ def test_world2(name):
 @pytest.mark.parametrize("name", sorted(WORLD4))
 def test_world4(name):
     rep = launch(4, dict(WORLD4[name]))
+    assert rep["max_grad_err"] < 3e-2
+
+
+@pytest.mark.parametrize("name", sorted(WORLD8))
+def test_world8(name):
+    rep = launch(8, dict(WORLD8[name]), timeout=900)
     assert rep["max_grad_err"] < 3e-2
