@@ -375,9 +375,13 @@ class CudaBackend:
             self.bg.gemm_bf16(a, b, out, m_, n_, k_, code, accumulate=accumulate)
         return out
 
-    def can_fuse_gemm_rs(self, m, n, group):
+    FUSE_MIN_K = 1536     # measured (profiles/r01_fused_gemm_rs_*): below this the GEMM outruns NVLink and fusion only adds latency
+
+    def can_fuse_gemm_rs(self, m, n, group, k=None):
         p = 1 if group is None else group.size
         if not self.fuse_gemm_rs or p < 2 or m % (p * 128) or n % 8:
+            return False
+        if k is not None and k < self.FUSE_MIN_K and os.environ.get("HGB_FUSE_GEMM_RS") != "force":
             return False
         buf = self._staging.get(tuple(group.ranks))
         tiles = (m // p // 128) * ((n + 255) // 256)
@@ -395,6 +399,7 @@ class CudaBackend:
         buf = self.staging(group, m_ * n_ * 2)
         out = torch.empty(m_ // group.size, n_, dtype=torch.bfloat16, device=a.device)
         self.comm.gemm_reduce_scatter(group, a, b, m_, n_, k_, code, buf, 0, buf.data_bytes, out)
+        self.n_fused_gemm_rs = getattr(self, "n_fused_gemm_rs", 0) + 1
         return out
 
     def rmsnorm_fwd(self, x, weight, eps):

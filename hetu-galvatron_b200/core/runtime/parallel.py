@@ -123,7 +123,8 @@ class ShardedUnit:
     """One layer's flat parameter, sharded over ``group`` (what an FSDP unit is in the reference)."""
 
     def __init__(self, module, group, dp_type, name="", tp_group=None, param_dtype=torch.bfloat16, reduce_in_fp32=False,
-                 sequence_parallel=False, init_seed=None, pool_slots=0, pool_grads=False):
+                 sequence_parallel=False, init_seed=None, pool_slots=0, pool_grads=False, load_module_func=None,
+                 all_block_name=None, load=None, distributed_checkpoint=False, reserve_save_buffer=False):
         assert dp_type in _DP_TYPES, dp_type
         be = get_backend()
         self.be, self.module, self.group, self.dp_type, self.name = be, module, group, dp_type, name
@@ -136,6 +137,8 @@ class ShardedUnit:
 
         # ---- materialise (meta -> device) and collect parameters ---------------------------------------------
         self._materialize(module, device, init_seed)
+        if load is not None and load_module_func is not None:
+            self._load(module, load_module_func, all_block_name, load, distributed_checkpoint)
         seen, params = set(), []
         for p in module.parameters():
             if id(p) not in seen:
@@ -194,6 +197,8 @@ class ShardedUnit:
         self._ln_params = [p for p in params if getattr(p, "sequence_parallel", False)] if (
             sequence_parallel and tp_group is not None and tp_group.size > 1) else []
 
+        if reserve_save_buffer:
+            be.reserve_checkpoint_gather(group, self.padded * 4)
         self.prediv, self.postdiv = fsdp_divide_factors(d)
         self._started = set()          # params whose G slice holds this step's gradient
         self._w_valid = self.w_pool is None
@@ -242,6 +247,18 @@ class ShardedUnit:
         self.g_flat = buf.view(self.reduce_dtype, self.padded)
         for p, off, n, shape in zip(self.params, self.offsets, self.numels, self.shapes):
             p._bg_grad = self.g_flat[off:off + n].view(shape)
+
+    def _load(self, module, load_module_func, all_block_name, load, distributed_checkpoint):
+        """The reference's ``param_init_fn`` with ``--load`` (parallel.py:79-89): every parameter-owning submodule of the
+        wrapped block is filled by the family's ``load_module_func(load, tp_group, name, submodule, block, distributed)``,
+        names relative to the block (``attention.attention.query_key_value`` ...)."""
+        kinds = tuple(all_block_name or ())
+        blocks = [m for m in module.modules() if kinds and isinstance(m, kinds)] or [module]
+        with torch.no_grad():
+            for block in blocks:
+                for name, sub in block.named_modules():
+                    if callable(getattr(sub, "reset_parameters", None)) and any(True for _ in sub.parameters(recurse=False)):
+                        load_module_func(load, self.tp_group, name, sub, block, distributed_checkpoint)
 
     # ---- step protocol ------------------------------------------------------------------------------------------------
     def begin_step(self, params_changed=True):

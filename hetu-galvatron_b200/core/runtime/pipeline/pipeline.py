@@ -183,7 +183,10 @@ class PipelineParallel(nn.Module):
             unit = ShardedUnit(module, dp_groups[i], dp_type, name="%s_%d" % (module_types[i], i), tp_group=tp_group,
                                param_dtype=mixed_precision, reduce_in_fp32=args.reduce_in_fp32,
                                sequence_parallel=self.sequence_parallel, init_seed=args.seed + 1000 * i,
-                               pool_slots=int(getattr(args, "zero3_pool_slots", 0)), pool_grads=pool_grads)
+                               pool_slots=int(getattr(args, "zero3_pool_slots", 0)), pool_grads=pool_grads,
+                               load_module_func=load_module_func, all_block_name=all_block_name, load=getattr(args, "load", None),
+                               distributed_checkpoint=bool(getattr(args, "distributed_checkpoint", False)),
+                               reserve_save_buffer=bool(getattr(args, "save", None)))
             self.units.append(unit)
             wrapped.append(DataParallelModule(module, unit, checkpoint=False))
         for a, b in zip(wrapped[:-1], wrapped[1:]):

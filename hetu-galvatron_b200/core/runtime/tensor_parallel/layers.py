@@ -77,7 +77,7 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
             ctx.sequence_parallel, ctx.allreduce_dgrad, ctx.tp_group = False, False, tp_group
             x2d = input.reshape(-1, input.shape[-1])
             n_out = weight.shape[0]
-            if getattr(be, "can_fuse_gemm_rs", None) and be.can_fuse_gemm_rs(x2d.shape[0], n_out, tp_group):
+            if getattr(be, "can_fuse_gemm_rs", None) and be.can_fuse_gemm_rs(x2d.shape[0], n_out, tp_group, x2d.shape[1]):
                 out = be.gemm_reduce_scatter(x2d, weight, "tn", tp_group)       # one fused operation
             else:
                 staged, _ = be.staging_tensor(tp_group, (x2d.shape[0], n_out), input.dtype)
@@ -114,7 +114,7 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
         grad_input = None
         if ctx.needs_input_grad[0]:
             m, k = dy2d.shape[0], weight.shape[1]
-            if ctx.sequence_parallel and getattr(be, "can_fuse_gemm_rs", None) and be.can_fuse_gemm_rs(m, k, group):
+            if ctx.sequence_parallel and getattr(be, "can_fuse_gemm_rs", None) and be.can_fuse_gemm_rs(m, k, group, dy2d.shape[1]):
                 # dgrad GEMM + reduce-scatter along the sequence (layers.py:462,488-494) as one fused operation
                 out = be.gemm_reduce_scatter(dy2d, weight, "nn", group)
                 grad_input = out.view(grad_output.shape[0] // group.size, *grad_output.shape[1:-1], k)

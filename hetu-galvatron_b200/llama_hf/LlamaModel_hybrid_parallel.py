@@ -1,6 +1,7 @@
 """Entry points of the family (``galvatron/models/llama_hf/LlamaModel_hybrid_parallel.py``)."""
 from ..core.runtime.hybrid_parallel_config import get_hybrid_parallel_configs_api
 from ..core.runtime.hybrid_parallel_model import construct_hybrid_parallel_model_api
+from .LlamaModel_checkpoint import load_llama_module
 from .LlamaModel_sequential import LlamaCls_, LlamaEmbeddings_, LlamaModelInfo, LlamaPreNorm_, construct_sequential_model
 from .LlamaModel_tensor_parallel import LlamaLayer_tp, LlamaSkeleton, construct_tensor_parallel_model
 from .meta_configs import config_from_meta, set_model_config
@@ -15,7 +16,7 @@ def construct_hybrid_parallel_model(model, model_config, training_args, hybrid_p
         model, model_config, training_args, hybrid_parallel_configs, LlamaModelInfo, construct_sequential_model,
         construct_tensor_parallel_model, wrap_block_name=[LlamaLayer_tp], wrap_checkpoint_block_name=[LlamaLayer_tp],
         wrap_other_block_name=[LlamaEmbeddings_, LlamaPreNorm_, LlamaCls_], layernorm_name=["LayerNorm", "norm"],
-        all_block_name=[LlamaEmbeddings_, LlamaLayer_tp, LlamaPreNorm_, LlamaCls_])
+        all_block_name=[LlamaEmbeddings_, LlamaLayer_tp, LlamaPreNorm_, LlamaCls_], load_module_func=load_llama_module)
 
 
 def get_llama_config(args, overwrite_args=True):

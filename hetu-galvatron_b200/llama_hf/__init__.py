@@ -1,4 +1,5 @@
 """The Llama family harness (``galvatron/models/llama_hf``): the three callbacks + ModelInfo the core API asks for."""
+from .LlamaModel_checkpoint import load_llama_module, save_llama_module
 from .LlamaModel_hybrid_parallel import (construct_hybrid_parallel_model, get_hybrid_parallel_configs, get_llama_config,
                                          llama_model_hp)
 from .LlamaModel_sequential import LlamaModelInfo, construct_sequential_model

@@ -83,6 +83,7 @@ def main():
     strategy = over.pop("_strategy_json", None)
     tol = over.pop("_tol", 3e-2)
     spec = over.pop("_spec", None)
+    golden_ckpt, save_to = over.pop("_golden_ckpt", None), over.pop("_save_to", None)
     use_cuda = os.environ.get("HOST_TEST_BACKEND", "oracle") == "cuda"
     from oracle import llama_ref
     from hetu_galvatron_b200 import smoke_model as sm
@@ -109,11 +110,33 @@ def main():
     w = assemble_full(model, config, world, rank, lambda u: u.read_full_params())
     w = {k: (v.cpu().clone() if torch.is_tensor(v) else [{kk: vv.cpu().clone() for kk, vv in lw.items()} for lw in v]) for k, v in w.items()}
 
+    report = {}
+    if golden_ckpt:   # the weights the model loaded must be HF's, bit for bit, whatever the tensor-parallel degree
+        hf = llama_ref.to_hf_state_dict(w, sm.oracle_cfg(config, args))
+        want = {}
+        for fname in sorted(os.listdir(golden_ckpt)):
+            if not fname.endswith(".pt"):
+                continue
+            blob = torch.load(os.path.join(golden_ckpt, fname), map_location="cpu", weights_only=True)
+            stem = fname[:-3]
+            for k, v in blob.items():
+                if stem == "lm_head":
+                    want["lm_head." + k] = v
+                elif stem == "model_embed_tokens":
+                    want["model." + k] = v
+                elif stem == "model_norm":
+                    want["model.norm." + k] = v
+                else:
+                    want["model.layers.%s.%s" % (stem.split("_")[-1], k)] = v
+        assert set(want) == set(hf), sorted(set(want) ^ set(hf))
+        bad = [k for k in want if not torch.equal(want[k].float(), hf[k].float())]
+        assert not bad, "loaded weights differ from the HF checkpoint: %s" % bad
+        report["ckpt_tensors_bit_exact"] = len(want)
+
     gbs, seq = args.global_train_batch_size, config.max_position_embeddings
     dp_group = model.vtp_data_group
     dp_idx, dp = dp_group.rank_in_group(rank), dp_group.size
     g = torch.Generator().manual_seed(11)
-    report = {}
     for it in range(2):
         x = torch.randint(0, config.vocab_size, (gbs, seq + 1), generator=g)
         tokens, labels = x[:, :-1].contiguous(), x[:, 1:].contiguous()
@@ -155,9 +178,12 @@ def main():
             lt = torch.tensor([loss if loss is not None else 0.0, 1.0 if loss is not None else 0.0], dtype=torch.float64, device=dev)
             dist.all_reduce(lt)
             mean_loss = float(lt[0] / lt[1])
-            report = {"loss": mean_loss, "ref_loss": float(ref_loss), "max_grad_err": max(errs.values()),
-                      "worst": max(errs, key=errs.get), "n_unshard": [u.n_unshard for u in model.model.units],
-                      "n_reduce": [u.n_reduce for u in model.model.units]}
+            report.update({"loss": mean_loss, "ref_loss": float(ref_loss), "max_grad_err": max(errs.values()),
+                           "worst": max(errs, key=errs.get), "n_unshard": [u.n_unshard for u in model.model.units],
+                           "n_reduce": [u.n_reduce for u in model.model.units]})
+            if save_to:   # the loaded (not yet updated) weights, in the reference's distributed layout
+                from hetu_galvatron_b200.llama_hf import save_llama_module
+                save_llama_module(save_to, model, opt, None, 0, args)
             if os.environ.get("HOST_TEST_DEBUG") and rank == 0:
                 def fit(a, b):
                     a, b = a.float().reshape(-1), b.float().reshape(-1)
@@ -180,6 +206,7 @@ def main():
                        for k, p in getattr(be, "_zero3_pools", {}).items()}
     if use_cuda:
         report["launches"] = be.launch_count()
+        report["fused_gemm_rs_calls"] = getattr(be, "n_fused_gemm_rs", 0)
     if rank == 0:
         print("HOST_TEST_REPORT " + json.dumps(report), flush=True)
     dist.barrier()

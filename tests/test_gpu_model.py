@@ -31,6 +31,8 @@ def test_two_gpus(name):
     _need(2)
     rep = launch(2, dict(WORLD2[name]), backend="cuda")
     assert rep["max_grad_err"] < 3e-2 and rep["launches"] > 0
+    if name == "tp2_megatron_sp_fused_gemm_rs":
+        assert rep["fused_gemm_rs_calls"] > 0
 
 
 @pytest.mark.parametrize("name", sorted(WORLD4))

@@ -16,8 +16,9 @@ _PORT = [29600]
 def launch(world, config, timeout=600, backend="oracle"):
     _PORT[0] += 1
     procs = []
+    extra_env = config.pop("_env", {})
     for rank in range(world):
-        env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+        env = dict(os.environ, **extra_env, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
                    MASTER_PORT=str(_PORT[0] + os.getpid() % 500), HOST_TEST_CONFIG=json.dumps(config), OMP_NUM_THREADS="2",
                    HOST_TEST_BACKEND=backend)
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_host_worker.py")], env=env,
@@ -46,6 +47,10 @@ WORLD2 = {
     "dp2_zero2_no_async_chunks2": dict(default_dp_type="zero2", chunks=2, async_grad_reduce=False),
     "tp2": dict(global_tp_deg=2, vocab_tp=2),
     "tp2_megatron_sp": dict(global_tp_deg=2, vocab_tp=2, sequence_parallel=True),
+    # shapes the fused GEMM+reduce-scatter accepts (M = 256 = p x 128): on the GPU the row-parallel forward and the
+    # column-parallel dgrad run as ONE kernel pair inside the model (forced: these K are below the profitability threshold)
+    "tp2_megatron_sp_fused_gemm_rs": dict(global_tp_deg=2, vocab_tp=2, sequence_parallel=True, _spec={"n_positions": 256},
+                                          _env={"HGB_FUSE_GEMM_RS": "force"}),
     "ulysses2": dict(global_tp_deg=2, use_ulysses=True, sequence_parallel=True, vocab_tp=2),
     "pp2_1f1b_chunks4": dict(pp_deg=2, chunks=4, pipeline_type="pipedream_flush", global_train_batch_size=8),
     "pp2_gpipe_chunks2": dict(pp_deg=2, chunks=2, pipeline_type="gpipe"),
