@@ -68,7 +68,10 @@ def main():
                 sp["all2all_size_%d_%dMB_time" % (n, mb)] = interp(a2a, mb) * scale
         ag = by.get(("all_gather_cast", src), [])
         if ag:
-            p2p["pp_size_%d" % n] = max(ag, key=lambda r: r["bytes"])["busGBps"] * src / (src - 1) / 2  # one-direction peer stores
+            # one-direction peer stores between two GPUs, measured at p=2 (the all-gather's bus bandwidth there IS the pairwise
+            # rate); NVSwitch gives every stage boundary the same link whatever the pipeline depth
+            pair = by.get(("all_gather_cast", 2), ag)
+            p2p["pp_size_%d" % n] = max(pair, key=lambda r: r["bytes"])["busGBps"]
     json.dump(ar, open(os.path.join(opts.out, "allreduce_bandwidth_1nodes_%dgpus_per_node.json" % N), "w"), indent=4)
     json.dump(sp, open(os.path.join(opts.out, "sp_time_1nodes_%dgpus_per_node.json" % N), "w"), indent=4)
     json.dump(p2p, open(os.path.join(opts.out, "p2p_bandwidth_1nodes_%dgpus_per_node.json" % N), "w"), indent=4)
