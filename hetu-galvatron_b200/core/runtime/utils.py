@@ -50,18 +50,59 @@ class FusedShardedAdamW(torch.optim.Optimizer):
         if self._fallback is not None:
             self._fallback.zero_grad(set_to_none)
 
+    def state_dict(self):
+        """Per-rank optimizer state (what ``optimizer/<rank>.pt`` of a distributed checkpoint holds): the moments live on the
+        sharded units, next to the fp32 shard the reduce-scatter epilogue updates."""
+        return {"fused_sharded_adamw": 1, "step_count": self.step_count,
+                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups],
+                "units": {u.name: {"exp_avg": u.exp_avg.detach().cpu(), "exp_avg_sq": u.exp_avg_sq.detach().cpu()}
+                          for u in self.units if u.uses_fused_optimizer()},
+                "fallback": None if self._fallback is None else self._fallback.state_dict()}
+
+    def load_state_dict(self, state):
+        if not state.get("fused_sharded_adamw"):
+            raise ValueError("not a FusedShardedAdamW state (saved with --optimizer torch?)")
+        self.step_count = int(state["step_count"])
+        for g, saved in zip(self.param_groups, state["param_groups"]):
+            g.update(saved)
+        for u in self.units:
+            if u.uses_fused_optimizer():
+                rec = state["units"][u.name]
+                u.exp_avg.copy_(rec["exp_avg"])
+                u.exp_avg_sq.copy_(rec["exp_avg_sq"])
+        if self._fallback is not None and state.get("fallback") is not None:
+            self._fallback.load_state_dict(state["fallback"])
+
+
+def _constant_lr(step):
+    return 1.0
+
 
 def get_optimizer_and_param_scheduler(model, args):
+    """``core/runtime/utils.py:140-167``: AdamW over the fp32 flat shards + the LR scheduler; with ``--distributed_checkpoint``
+    both resume from ``<load>/iter_<load_iteration>/{optimizer/<rank>.pt, opt_param_scheduler.json}`` (:152-165)."""
     if getattr(args, "fused_optimizer", False):
-        opt = FusedShardedAdamW(model, lr=args.lr, betas=(getattr(args, "adam_beta1", 0.9), getattr(args, "adam_beta2", 0.999)),
-                                eps=getattr(args, "adam_eps", 1e-8), weight_decay=args.adam_weight_decay)
-        return opt, torch.optim.lr_scheduler.LambdaLR(opt, lambda step: 1.0)
-    params = list(model.parameters())
-    fused = all(p.is_cuda for p in params)
-    optimizer = torch.optim.AdamW(params, lr=args.lr, weight_decay=args.adam_weight_decay,
-                                  betas=(getattr(args, "adam_beta1", 0.9), getattr(args, "adam_beta2", 0.999)),
-                                  eps=getattr(args, "adam_eps", 1e-8), fused=fused)
-    scheduler = torch.optim.lr_scheduler.LambdaLR(optimizer, lambda step: 1.0)   # constant LR (random-data scripts)
+        optimizer = FusedShardedAdamW(model, lr=args.lr, betas=(getattr(args, "adam_beta1", 0.9), getattr(args, "adam_beta2", 0.999)),
+                                      eps=getattr(args, "adam_eps", 1e-8), weight_decay=args.adam_weight_decay)
+    else:
+        params = list(model.parameters())
+        optimizer = torch.optim.AdamW(params, lr=args.lr, weight_decay=args.adam_weight_decay,
+                                      betas=(getattr(args, "adam_beta1", 0.9), getattr(args, "adam_beta2", 0.999)),
+                                      eps=getattr(args, "adam_eps", 1e-8), fused=all(p.is_cuda for p in params))
+    scheduler = torch.optim.lr_scheduler.LambdaLR(optimizer, _constant_lr)   # constant LR (random-data scripts)
+    if getattr(args, "distributed_checkpoint", False) and getattr(args, "load", None):
+        import json
+        import os
+        from .backend import get_backend
+        root = os.path.join(args.load, "iter_%d" % int(getattr(args, "load_iteration", 0)))
+        opt_file = os.path.join(root, "optimizer", "%d.pt" % get_backend().rank)
+        if os.path.exists(opt_file):
+            optimizer.load_state_dict(torch.load(opt_file, map_location="cpu", weights_only=True))
+        sched_file = os.path.join(root, "opt_param_scheduler.json")
+        if os.path.exists(sched_file):
+            saved = json.load(open(sched_file))
+            if saved:
+                scheduler.load_state_dict(saved)
     return optimizer, scheduler
 
 

@@ -84,6 +84,7 @@ def main():
     tol = over.pop("_tol", 3e-2)
     spec = over.pop("_spec", None)
     golden_ckpt, save_to = over.pop("_golden_ckpt", None), over.pop("_save_to", None)
+    save_after, n_iters, skip_batches = over.pop("_save_after", 0), over.pop("_iters", 2), over.pop("_skip_batches", 0)
     use_cuda = os.environ.get("HOST_TEST_BACKEND", "oracle") == "cuda"
     from oracle import llama_ref
     from hetu_galvatron_b200 import smoke_model as sm
@@ -106,7 +107,7 @@ def main():
         over["galvatron_config_path"] = strategy
     args = sm.tiny_args(**over)
     config, model = sm.build(args, dict(sm.TINY, **spec) if spec else None)
-    opt, _ = get_optimizer_and_param_scheduler(model, args)
+    opt, sched = get_optimizer_and_param_scheduler(model, args)
     w = assemble_full(model, config, world, rank, lambda u: u.read_full_params())
     w = {k: (v.cpu().clone() if torch.is_tensor(v) else [{kk: vv.cpu().clone() for kk, vv in lw.items()} for lw in v]) for k, v in w.items()}
 
@@ -137,7 +138,17 @@ def main():
     dp_group = model.vtp_data_group
     dp_idx, dp = dp_group.rank_in_group(rank), dp_group.size
     g = torch.Generator().manual_seed(11)
-    for it in range(2):
+    for _ in range(skip_batches):      # resume: the batches the saved run already consumed
+        torch.randint(0, config.vocab_size, (gbs, seq + 1), generator=g)
+    report["losses"] = []
+
+    def save_now(step):
+        from hetu_galvatron_b200.llama_hf import save_llama_module
+        save_llama_module(save_to, model, opt, sched, step, args)
+
+    for it in range(n_iters):
+        if save_to and save_after == it and it > 0:
+            save_now(it)
         x = torch.randint(0, config.vocab_size, (gbs, seq + 1), generator=g)
         tokens, labels = x[:, :-1].contiguous(), x[:, 1:].contiguous()
         lo, hi = dp_idx * gbs // dp, (dp_idx + 1) * gbs // dp
@@ -181,9 +192,9 @@ def main():
             report.update({"loss": mean_loss, "ref_loss": float(ref_loss), "max_grad_err": max(errs.values()),
                            "worst": max(errs, key=errs.get), "n_unshard": [u.n_unshard for u in model.model.units],
                            "n_reduce": [u.n_reduce for u in model.model.units]})
-            if save_to:   # the loaded (not yet updated) weights, in the reference's distributed layout
-                from hetu_galvatron_b200.llama_hf import save_llama_module
-                save_llama_module(save_to, model, opt, None, 0, args)
+            report["losses"].append(mean_loss)
+            if save_to and save_after == 0:   # the loaded (not yet updated) weights, in the reference's distributed layout
+                save_now(0)
             if os.environ.get("HOST_TEST_DEBUG") and rank == 0:
                 def fit(a, b):
                     a, b = a.float().reshape(-1), b.float().reshape(-1)
@@ -198,7 +209,9 @@ def main():
         else:
             lt = torch.tensor([loss if loss is not None else 0.0, 1.0 if loss is not None else 0.0], dtype=torch.float64, device=dev)
             dist.all_reduce(lt)
-            report["loss_step1"] = float(lt[0] / lt[1])       # after one optimizer update: re-gathered parameters
+            report["losses"].append(float(lt[0] / lt[1]))
+            if it == 1:
+                report["loss_step1"] = report["losses"][-1]       # after one optimizer update: re-gathered parameters
         opt.step()
         opt.zero_grad()
     report["n_unshard_2steps"] = [u.n_unshard for u in model.model.units]

@@ -56,3 +56,16 @@ def test_save_then_load_distributed_checkpoint(name, tmp_path):
     # ... and it loads back (load_distributed_checkpoint :27-45) to HF's weights
     rep = launch(world, dict(over, load=out, distributed_checkpoint=True, _golden_ckpt=GOLDEN))
     assert rep["ckpt_tensors_bit_exact"] == 21
+
+
+@pytest.mark.parametrize("name,optimizer", [("dp2_zero3", "torch"), ("dp2_zero3", "fused"), ("tp2", "torch")])
+def test_resume_is_bit_identical(name, optimizer, tmp_path):
+    """Train 2 steps, save (weights + per-rank optimizer state + scheduler, core/runtime/utils.py:152-165), train a third; a
+    fresh job that loads the checkpoint and trains that third step must see the same loss to the last bit."""
+    world, over = CASES[name]
+    over = dict(over, fused_optimizer=optimizer == "fused")
+    out = str(tmp_path / "ckpt")
+    a = launch(world, dict(over, load=GOLDEN, save=out, _save_to=out, _save_after=2, _iters=3))
+    assert len(a["losses"]) == 3 and a["losses"][2] != a["losses"][0]
+    b = launch(world, dict(over, load=out, distributed_checkpoint=True, load_iteration=2, _skip_batches=2, _iters=1))
+    assert b["losses"][0] == a["losses"][2], (a["losses"], b["losses"])

@@ -68,3 +68,19 @@ def test_fused_gemm_reduce_scatter(n):
                           "127.0.0.1", "--master-port", str(29800 + n), os.path.join(root, "scripts", "test_fused_gemm_rs.py")],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "FUSED_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("world,name", [(1, "tp1"), (2, "tp2"), (2, "dp2_zero3")])
+def test_checkpoint_load_save_resume(world, name, tmp_path):
+    """Product path: load the reference-converted HF checkpoint (bit-exact), train 2 steps, save in the reference's distributed
+    layout (fp32 gather through the C ABI), resume in a fresh job: the third step's loss must match the uninterrupted run."""
+    _need(world)
+    import json
+    from test_checkpoint import CASES, EXPECTED, GOLDEN
+    over = dict(CASES[name][1], fused_optimizer=True)
+    out = str(tmp_path / "ckpt")
+    a = launch(world, dict(over, load=GOLDEN, save=out, _golden_ckpt=GOLDEN, _save_to=out, _save_after=2, _iters=3), backend="cuda")
+    assert a["ckpt_tensors_bit_exact"] == 21
+    assert abs(a["losses"][0] - EXPECTED["hf_loss_fp32"]) <= 5e-3 * EXPECTED["hf_loss_fp32"]
+    b = launch(world, dict(over, load=out, distributed_checkpoint=True, load_iteration=2, _skip_batches=2, _iters=1), backend="cuda")
+    assert abs(b["losses"][0] - a["losses"][2]) <= 1e-6 * abs(a["losses"][2]), (a["losses"], b["losses"], json.dumps(over))
