@@ -293,41 +293,51 @@ def run_ours(opts):
 # ---------------------------------------------------------------------------------------------------------------------
 def cpu_reference_sample(opts, budget_s=25.0):
     """The CPU restatement of the reference path (oracle backend, all host threads) on a bounded sample of the workload:
-    Llama-3-8B shapes, ONE transformer layer + embedding + lm_head, seq 1024, batch 1.  Reported as measured tokens/s of
-    that sample plus the per-layer-token extrapolation to 32 layers (never a like-for-like 8B number)."""
+    Llama-3-8B shapes, embedding + lm_head + ONE and then TWO transformer layers, seq 1024, batch 1.  The two samples separate
+    the per-layer cost from the embedding/head cost; ``value`` is the full-depth (32-layer) tokens/s they imply -- an
+    extrapolation that favours the CPU (seq 1024 instead of 8192: 8x less attention work per token), labelled as such, never a
+    like-for-like 8B measurement."""
     import torch
     from oracle.gloo_backend import OracleBackend
     from hetu_galvatron_b200.core.runtime.backend import reset_backend, set_backend
     from hetu_galvatron_b200.core.runtime.utils import get_optimizer_and_param_scheduler
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    set_backend(OracleBackend())
-    sample = argparse.Namespace(**vars(opts))
-    sample.layers, sample.seq, sample.optimizer, sample.checkpoint_layers = 1, 1024, "torch", -1
-    strategy = {"pp_deg": 1, "tp_sizes_enc": "1", "tp_consecutive_flags": "1", "dp_types_enc": "0", "use_sp": "0", "checkpoint": "0",
-                "global_bsz": 1, "chunks": 1, "default_dp_type": "zero2", "vtp": 1}
-    args, config, model = build_model(sample, strategy)
-    opt, _ = get_optimizer_and_param_scheduler(model, args)
-    batches = synthetic_batches(args, config, 3, 0, 1, pin=False)
-    times = []
-    t_start = time.perf_counter()
-    for i, (t, l) in enumerate(batches):
-        t0 = time.perf_counter()
-        model.forward_backward([t], i, None, loss_func=None, attention_mask=None, labels=l)
-        opt.step(); opt.zero_grad()
-        times.append(time.perf_counter() - t0)
-        if time.perf_counter() - t_start > budget_s and i >= 1:
-            break
-    step_s = min(times[1:]) if len(times) > 1 else times[0]
-    tok = config.max_position_embeddings
-    # per-token cost of the sample = head/embedding part + 1 layer; extrapolate the layer part to the full depth
+
+    def best_step(n_layers, budget):
+        set_backend(OracleBackend())
+        sample = argparse.Namespace(**vars(opts))
+        sample.layers, sample.seq, sample.optimizer, sample.checkpoint_layers = n_layers, 1024, "torch", -1
+        one = ",".join(["1"] * n_layers)
+        zero = ",".join(["0"] * n_layers)
+        strategy = {"pp_deg": 1, "tp_sizes_enc": one, "tp_consecutive_flags": one, "dp_types_enc": zero, "use_sp": zero,
+                    "checkpoint": zero, "global_bsz": 1, "chunks": 1, "default_dp_type": "zero2", "vtp": 1}
+        args, config, model = build_model(sample, strategy)
+        opt, _ = get_optimizer_and_param_scheduler(model, args)
+        batches = synthetic_batches(args, config, 3, 0, 1, pin=False)
+        times, t_start = [], time.perf_counter()
+        for i, (t, l) in enumerate(batches):
+            t0 = time.perf_counter()
+            model.forward_backward([t], i, None, loss_func=None, attention_mask=None, labels=l)
+            opt.step(); opt.zero_grad()
+            times.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_start > budget and i >= 1:
+                break
+        reset_backend()
+        return (min(times[1:]) if len(times) > 1 else times[0]), len(times), config.max_position_embeddings
+
+    t1, n1, tok = best_step(1, budget_s * 0.4)
+    t2, n2, _ = best_step(2, budget_s * 0.6)
+    layer_s = max(t2 - t1, 0.05 * t1)
+    other_s = max(t1 - layer_s, 0.0)
     full_layers = 32
-    reset_backend()
-    return {"value": round(tok / step_s, 2), "unit": "tokens/s", "cores": cores, "kind": "port",
-            "sample": "oracle CPU restatement (fp32 compute, bf16 storage): Llama-3-8B shapes, 1 of 32 layers + embedding + lm_head, "
-                      "seq 1024, batch 1, %d step(s), best step %.2f s" % (len(times), step_s),
-            "extrapolated_full_depth_tokens_per_s": round(tok / (step_s * full_layers), 3),
-            "note": "extrapolation assumes the 1-layer sample cost scales with depth (upper bound on CPU speed); not a like-for-like number"}
+    full_s = other_s + full_layers * layer_s
+    return {"value": round(tok / full_s, 3), "unit": "tokens/s", "cores": cores, "kind": "port",
+            "sample": "oracle CPU restatement (fp32 compute, bf16 storage), Llama-3-8B shapes, seq 1024, batch 1: embedding + lm_head + "
+                      "1 layer (%d steps, best %.2f s) and + 2 layers (%d steps, best %.2f s) -> %.2f s per layer, %.2f s for the rest; "
+                      "value = 1024 tokens / (rest + 32 layers) = extrapolated full-depth rate, NOT a like-for-like seq-8192 run"
+                      % (n1, t1, n2, t2, layer_s, other_s),
+            "sample_tokens_per_s_1layer": round(tok / t1, 2)}
 
 
 def run_reference(opts):
@@ -337,7 +347,9 @@ def run_reference(opts):
     if rank != 0:
         return
     K = max(1, opts.steps)
-    base = cpu_reference_sample(opts, budget_s=20.0 * K)
+    from hetu_galvatron_b200.core.runtime import world as _world
+    with _world.simulated(0, 1):        # under torchrun the env says world N; the CPU sample is a single-process job
+        base = cpu_reference_sample(opts, budget_s=20.0 * K)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "tokens/s", "n_gpus": opts.gpus, "steps": opts.steps,
             "warmup": opts.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 storage / fp32 compute",
             "data": "synthetic tokens (DataLoaderForLlama generator, seed 1234), random-init weights",
