@@ -476,6 +476,14 @@ class CudaBackend:
                                                scale=softmax_scale, enable_gqa=k.shape[2] != q.shape[2])
         return o.transpose(1, 2)
 
+    def attention_prefix(self, q, k, v, softmax_scale):
+        """Causal attention of a query block against a LONGER key/value prefix, diagonal aligned to the bottom-right corner
+        (query i sees keys j <= i + sk - sq): one zigzag chunk of a context-parallel rank against everything before it.
+        Library call, as all attention here: flash-attn 2 (its causal mask has exactly this alignment for sq != sk; torch's
+        SDPA aligns top-left).  q [b,sq,n,d], k/v [b,sk,ng,d].  Differentiable."""
+        from flash_attn import flash_attn_func
+        return flash_attn_func(q, k, v, dropout_p=0.0, softmax_scale=softmax_scale, causal=True)
+
     def attention_fwd(self, q, k, v, causal, softmax_scale):
         """flash-attn 2 library call (the reference's choice); used when HGB_ATTN=flash."""
         from flash_attn.flash_attn_interface import _flash_attn_forward

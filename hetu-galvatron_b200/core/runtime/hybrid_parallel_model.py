@@ -168,7 +168,8 @@ def construct_hybrid_parallel_model_api(model, model_config, training_args, hybr
     # peer-visible activation staging for every group this rank communicates over, pipeline transport slots, then one
     # exchange of arena offsets for the whole job (replaces all NCCL communicator bootstraps)
     _reserve_activation_staging(be, args, info, hp_whole, hp_model, tp_groups_whole, sp_groups_whole, split_tp_sp_cp_groups_whole,
-                                allgather_tp_sp_cp_groups_whole, fused_allgather_groups_whole, fused_split_groups_whole)
+                                allgather_tp_sp_cp_groups_whole, fused_allgather_groups_whole, fused_split_groups_whole,
+                                cp_groups_whole)
     finalize_pools(be)
     be.exchange()
 
@@ -181,7 +182,7 @@ def construct_hybrid_parallel_model_api(model, model_config, training_args, hybr
 
 
 def _reserve_activation_staging(be, args, info, hp_whole, hp_model, tp_groups, sp_groups, split_sep_groups, allgather_sep_groups,
-                                fused_ag_groups, fused_sp_groups):
+                                fused_ag_groups, fused_sp_groups, cp_groups=None):
     """Size one staging buffer per communicating group from the boundary shapes: the largest activation message is
     seq x microbatch x hidden (bf16), the logits-side reductions are [seq x microbatch] fp32 pairs."""
     world = _world.get_world_size()
@@ -203,6 +204,7 @@ def _reserve_activation_staging(be, args, info, hp_whole, hp_model, tp_groups, s
             be.reserve_staging(g, act)
 
     for i in range(s0, s1):
-        for lst in (tp_groups, sp_groups, split_sep_groups, allgather_sep_groups, fused_ag_groups, fused_sp_groups):
-            reserve(lst[i])
+        for lst in (tp_groups, sp_groups, split_sep_groups, allgather_sep_groups, fused_ag_groups, fused_sp_groups, cp_groups or ()):
+            if lst:
+                reserve(lst[i])
     hp_model.reserve_transport(max_mbs)

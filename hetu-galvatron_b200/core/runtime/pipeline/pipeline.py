@@ -268,10 +268,12 @@ class PipelineParallel(nn.Module):
         for mb in (microbatches[0][0], microbatches[0][-1]):
             shape = copy.deepcopy(template_tensor_shape)
             mbs = mb[0].shape[0] * dp_size_input // dp_size
-            size = (sp_size if tp_size == 1 else tp_size) * cp_size
+            # context parallelism always splits the sequence; tp|sp only under --sequence-parallel (the reference divides by
+            # neither without the flag, :277-281, which leaves cp x pp without sequence parallelism broken there)
+            size = (sp_size if tp_size == 1 else tp_size) * cp_size if self.sequence_parallel else cp_size
             for i in range(len(shape)):
                 shape[i] = [mbs if d == -1 else d for d in shape[i]]
-                if self.sequence_parallel:
+                if size > 1:
                     if self.shape_order == "SBH":
                         shape[i][0] = shape[i][0] // size
                     else:

@@ -133,6 +133,46 @@ class _FlashAttnFn(torch.autograd.Function):
         return dq, dk, dv, None, None
 
 
+class _CpGatherKvFn(torch.autograd.Function):
+    """Context parallelism, K or V: this rank's two zigzag chunks [b, s/c, ng, d] -> the whole sequence in natural token order
+    [b, s, ng, d] (all-gather over the cp group + un-zigzag); backward re-applies the zigzag order and reduce-scatters the
+    gradient (the reference's ring passes the same bytes around hop by hop, transformer.py:2252-2680)."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        from ..redistribute import _reverse_zigzag_transformation
+        b, s_loc, ng, d = x.shape
+        ctx.group, ctx.dims = group, (b, s_loc, ng, d)
+        rows = x.transpose(0, 1).contiguous().reshape(s_loc, b * ng * d)
+        full = get_backend().all_gather_first_dim(rows, group)                       # rank-major chunk order
+        full = _reverse_zigzag_transformation(full, group.size)
+        return full.reshape(group.size * s_loc, b, ng, d).transpose(0, 1).contiguous()
+
+    @staticmethod
+    def backward(ctx, grad):
+        from ..redistribute import _zigzag_transformation
+        b, s_loc, ng, d = ctx.dims
+        c = ctx.group.size
+        rows = grad.transpose(0, 1).contiguous().reshape(c * s_loc, b * ng * d)
+        rows = _zigzag_transformation(rows, c)
+        out = get_backend().reduce_scatter_first_dim(rows, ctx.group)
+        return out.reshape(s_loc, b, ng, d).transpose(0, 1).contiguous(), None
+
+
+def _cp_attention(q, k, v, group, scale):
+    """Causal self-attention under zigzag context parallelism: the rank holds token chunks (r, 2c-1-r); each chunk attends
+    the gathered keys/values up to its own end."""
+    be = get_backend()
+    c, r = group.size, group.rank_in_group()
+    k_full, v_full = _CpGatherKvFn.apply(k, group), _CpGatherKvFn.apply(v, group)
+    half = q.shape[1] // 2
+    outs = []
+    for q_blk, chunk in ((q[:, :half], r), (q[:, half:], 2 * c - 1 - r)):
+        end = (chunk + 1) * half
+        outs.append(be.attention_prefix(q_blk, k_full[:, :end], v_full[:, :end], scale))
+    return torch.cat(outs, 1)
+
+
 def _attention(q, k, v, causal, scale):
     be = get_backend()
     fn = getattr(be, "attention", None)
@@ -174,8 +214,9 @@ class ParallelAttention(nn.Module):
         super().__init__()
         if attention_type != AttnType.self_attn:
             raise NotImplementedError("only self attention is on the Galvatron hot path")
-        if use_zigzag_cp or _size(cp_group) > 1:
-            raise NotImplementedError("context parallelism (zigzag ring attention) is SURVEY 8(f) 'next', not built yet")
+        self.use_cp = bool(use_zigzag_cp) or _size(cp_group) > 1
+        if self.use_cp and use_ulysses and _size(sp_group) > 1:
+            raise NotImplementedError("context parallelism together with Ulysses on the same layer is not supported")
         self.layer_number = max(1, layer_number)
         self.attn_mask_type = attn_mask_type
         self.tp_group, self.sp_group, self.cp_group = tp_group, sp_group, cp_group
@@ -212,6 +253,9 @@ class ParallelAttention(nn.Module):
             q, k, v = _UlyssesFn.apply(self.sp_group, True, q, k, v)       # [b, s, n/p, hn]
             ctxt = _attention(q, k, v, causal, self.softmax_scale)
             (ctxt,) = _UlyssesFn.apply(self.sp_group, False, ctxt)         # [b, s/p, n, hn]
+        elif self.use_cp:
+            assert causal, "context parallelism is implemented for causal self-attention"
+            ctxt = _cp_attention(q, k, v, self.cp_group, self.softmax_scale)   # [b, s/c, np, hn]
         else:
             ctxt = _attention(q, k, v, causal, self.softmax_scale)          # [b, s, np, hn]
         b, s = ctxt.shape[0], ctxt.shape[1]

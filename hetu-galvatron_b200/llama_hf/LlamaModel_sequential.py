@@ -15,6 +15,18 @@ def _size(g):
     return 1 if g is None else g.size
 
 
+def _zigzag_local(x, group):
+    """[b, s] tokens / labels -> this context-parallel rank's two zigzag chunks (r, 2c-1-r) [b, s/c].  The reference's real-data
+    loader does this slicing before the model (Megatron ``get_batch_on_this_cp_rank``, models/llama_hf/dataloader.py:151);
+    here the first and the last layer do it, so ``forward_backward`` takes the same full-sequence batch in every mode."""
+    c = _size(group)
+    if c == 1:
+        return x
+    r, half = group.rank_in_group(), x.shape[1] // (2 * c)
+    assert half * 2 * c == x.shape[1], "sequence length must be a multiple of 2 x the context-parallel degree"
+    return torch.cat([x[:, r * half:(r + 1) * half], x[:, (2 * c - 1 - r) * half:(2 * c - r) * half]], 1).contiguous()
+
+
 class LlamaEmbeddings_(nn.Module):
     def __init__(self, model):
         super().__init__()
@@ -30,6 +42,7 @@ class LlamaEmbeddings_(nn.Module):
                 seq, self.sp_group.rank_in_group() if _size(self.sp_group) > 1 else 0, _size(self.sp_group))
 
     def forward(self, tokens, position_ids=None, attention_mask=None, labels=None):
+        tokens = _zigzag_local(tokens, self.cp_group)
         if self.vocab_sp:
             tokens = tokens[:, self.seq_start_index:self.seq_end_index].contiguous()
         hidden_states = self.embed_tokens(tokens)
@@ -94,6 +107,7 @@ class LlamaCls_(nn.Module):
                 seq, self.sp_group.rank_in_group() if _size(self.sp_group) > 1 else 0, _size(self.sp_group))
 
     def forward(self, hidden_states, position_ids=None, attention_mask=None, labels=None):
+        labels = _zigzag_local(labels, self.cp_group)
         if self.vocab_sp:
             labels = labels[:, self.seq_start_index:self.seq_end_index].contiguous()
         # (without SP the dgrad all-reduce of copy_to_tensor_model_parallel_region :146-147 happens inside the linear)

@@ -51,6 +51,16 @@ class LlamaAttention_tp(nn.Module):
                                                               torch.bfloat16 if get_args().mixed_precision == "bf16" else torch.float32, device)
         return self._rope_cache[key]
 
+    def _rope_zigzag(self, local_seq, device):
+        key = ("zigzag", local_seq)
+        if key not in self._rope_cache:
+            c, r = self.cp_size, self.cp_group.rank_in_group()
+            cos, sin = self._rope(local_seq * c, 0, device)
+            half = local_seq // 2
+            idx = torch.cat([torch.arange(r * half, (r + 1) * half), torch.arange((2 * c - 1 - r) * half, (2 * c - r) * half)]).to(device)
+            self._rope_cache[key] = (cos[idx].contiguous(), sin[idx].contiguous())
+        return self._rope_cache[key]
+
     def forward(self, hidden_states, attention_mask):
         residual = hidden_states
         hidden_states = self.LayerNorm(hidden_states)
@@ -63,7 +73,12 @@ class LlamaAttention_tp(nn.Module):
             seq, offset = s_local * self.tp_group.size, 0
         else:
             seq, offset = s_local, 0
-        rope = self._rope(seq, offset, hidden_states.device)
+        if self.use_zigzag_cp:
+            # zigzag context parallelism: this rank's `seq` tokens are chunks (r, 2c-1-r) of the c*seq-token sequence; RoPE takes
+            # their global positions (the reference lets Megatron's RotaryEmbedding pick them, LlamaModel_tensor_parallel.py:59-63)
+            rope = self._rope_zigzag(seq, hidden_states.device)
+        else:
+            rope = self._rope(seq, offset, hidden_states.device)
         out, _ = self.attention(hidden_states, attention_mask, rotary_pos_emb=rope)
         return out + residual
 

@@ -273,6 +273,17 @@ class OracleBackend:
         dk = self._rot(dk, cos, sin, True)
         return torch.cat([dq, dk, dv.float()], dim=3).reshape(s, b, ng * (r + 2) * hn).to(dv.dtype)
 
+    def attention_prefix(self, q, k, v, softmax_scale):
+        """query i attends keys j <= i + (sk - sq) (bottom-right aligned causal mask); plain differentiable torch math."""
+        rep = q.shape[2] // k.shape[2]
+        qf, kf, vf = q.float(), k.float().repeat_interleave(rep, 2), v.float().repeat_interleave(rep, 2)
+        qf, kf, vf = [t.transpose(1, 2) for t in (qf, kf, vf)]
+        sq, sk = qf.shape[-2], kf.shape[-2]
+        scores = qf @ kf.transpose(-1, -2) * softmax_scale
+        mask = torch.arange(sk)[None, :] > (torch.arange(sq)[:, None] + (sk - sq))
+        p = torch.softmax(scores.masked_fill(mask, float("-inf")), -1)
+        return (p @ vf).transpose(1, 2).contiguous().to(q.dtype)
+
     def attention_fwd(self, q, k, v, causal, softmax_scale):
         rep = q.shape[2] // k.shape[2]
         qf, kf, vf = q.float(), k.float().repeat_interleave(rep, 2), v.float().repeat_interleave(rep, 2)

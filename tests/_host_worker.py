@@ -171,7 +171,9 @@ def main():
             # is averaged over that layer's SDP group (FSDP) -- so a layer whose SDP group is larger than the loss's
             # data-parallel degree (Ulysses: DPxSP; a tp=1 layer feeding a tp>1 head through relocation) ends up with
             # dp_cls / |sdp_layer| times the true mean gradient.  Invisible under Adam; see DESIGN.md "reference quirks".
-            dp_cls = model.hp_configs_whole["dp_sizes_whole"][-1]
+            # (context-parallel ranks each average over their OWN tokens, so their gradients do add up to the global mean: the cp
+            # degree of the loss row counts like data parallelism)
+            dp_cls = model.hp_configs_whole["dp_sizes_whole"][-1] * model.hp_configs_whole["cp_sizes_whole"][-1]
             scale = {}
             units_all = [None] * world
             dist.all_gather_object(units_all, {u.name: u.group.size for u in model.model.units})

@@ -46,6 +46,8 @@ WORLD2 = {
     "dp2_zero3_pool2_no_async_chunks2": dict(sdp=1, embed_sdp=1, zero3_pool_slots=2, chunks=2, async_grad_reduce=False),
     "dp2_zero2_no_async_chunks2": dict(default_dp_type="zero2", chunks=2, async_grad_reduce=False),
     "tp2": dict(global_tp_deg=2, vocab_tp=2),
+    # context parallelism: zigzag token chunks, keys/values gathered over the cp group, per-chunk causal attention
+    "cp2": dict(global_cp_deg=2, vocab_cp=2),
     "tp2_megatron_sp": dict(global_tp_deg=2, vocab_tp=2, sequence_parallel=True),
     # shapes the fused GEMM+reduce-scatter accepts (M = 256 = p x 128): on the GPU the row-parallel forward and the
     # column-parallel dgrad run as ONE kernel pair inside the model (forced: these K are below the profitability threshold)
@@ -70,6 +72,9 @@ WORLD4 = {
                                    chunks=2, global_train_batch_size=8),
     # BASELINE config (5) shape: ZeRO-3 on every layer + activation checkpointing
     "baseline5_zero3_ckpt_dp4": dict(sdp=1, global_checkpoint=1, embed_sdp=1, chunks=1, global_train_batch_size=8),
+    "cp2_dp2_zero3_ckpt": dict(global_cp_deg=2, vocab_cp=2, sdp=1, global_checkpoint=1, chunks=2, global_train_batch_size=8),
+    "cp2_pp2_1f1b": dict(global_cp_deg=2, vocab_cp=2, pp_deg=2, chunks=2, pipeline_type="pipedream_flush"),
+    "cp2_tp2_megatron_sp": dict(global_cp_deg=2, vocab_cp=2, global_tp_deg=2, vocab_tp=2, sequence_parallel=True),
     "hybrid_mixed": dict(sequence_parallel=True, _spec={"n_kv_heads": 4},
                          _strategy_json={"pp_deg": 1, "tp_sizes_enc": "2,4", "tp_consecutive_flags": "1,1", "dp_types_enc": "1,0",
                                          "use_sp": "1,0", "checkpoint": "0,1", "global_bsz": 8, "chunks": 2,
