@@ -48,6 +48,15 @@ SIGNATURES = {
     "bg_arena_attach_local": (_i, [_vp, _i, _vp]),
     "bg_ctx_error_flag": (_i, [_vp, _c.POINTER(_i)]),
     "bg_ctx_error_info": (_i, [_vp, _c.POINTER(_i)]),
+    "bg_ctx_create_ex": (_i, [_i, _i, _i, _sz, _c.c_uint, _c.POINTER(_vp)]),
+    "bg_arena_alloc_aligned": (_i, [_vp, _sz, _sz, _c.POINTER(_sz)]),
+    "bg_arena_mode": (_i, [_vp, _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_sz)]),
+    "bg_arena_export_fd": (_i, [_vp, _c.POINTER(_i)]),
+    "bg_arena_import_fd": (_i, [_vp, _i, _i]),
+    "bg_group_mc_create": (_i, [_vp, _i, _sz, _c.POINTER(_i)]),
+    "bg_group_mc_join": (_i, [_vp, _i, _i, _sz]),
+    "bg_group_mc_bind": (_i, [_vp, _i, _sz]),
+    "bg_all_reduce_nvls": (_i, [_vp, _i, _i, _sz, _vp, _sz, _i, _c.c_float, _vp]),
     "bg_group_create": (_i, [_vp, _c.POINTER(_i), _i, _c.POINTER(_i)]),
     "bg_group_info": (_i, [_vp, _i, _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i)]),
     "bg_build_groups": (_i, [_i, _i, _i, _i, _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i),
@@ -171,6 +180,54 @@ class SymBuffer:
         return (_sz * len(base))(*[int(o) + int(byte_offset) for o in base])
 
 
+class _FdChannel:
+    """POSIX file descriptors between the processes of one node: a listening unix socket per rank, SCM_RIGHTS messages
+    tagged (source rank, tag).  Used for the VMM arena handles and the multicast objects (a cudaIpc handle cannot carry
+    either).  The socket paths travel over the bootstrap process group."""
+
+    def __init__(self, rank, world, pg=None):
+        import socket
+        import tempfile
+        import torch.distributed as dist
+        self.rank, self.world = rank, world
+        self.path = os.path.join(tempfile.gettempdir(), "hgb_fd_%d_%d_%d.sock" % (os.getuid(), os.getpid(), rank))
+        if os.path.exists(self.path):
+            os.unlink(self.path)
+        self.srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        self.srv.bind(self.path)
+        self.srv.listen(max(8, world))
+        paths = [None] * world
+        dist.all_gather_object(paths, self.path, group=pg)
+        self.paths = paths
+
+    def exchange(self, outgoing, n_expected):
+        """outgoing: [(dest_rank, tag, fd)]; returns {(src_rank, tag): fd} for ``n_expected`` incoming descriptors."""
+        import pickle
+        import socket
+        import threading
+
+        def send_all():
+            for dest, tag, fd in outgoing:
+                with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as s:
+                    s.connect(self.paths[dest])
+                    socket.send_fds(s, [pickle.dumps((self.rank, tag))], [fd])
+        sender = threading.Thread(target=send_all)
+        sender.start()
+        got = {}
+        while len(got) < n_expected:
+            conn, _ = self.srv.accept()
+            with conn:
+                msg, fds, _, _ = socket.recv_fds(conn, 4096, 1)
+                got[pickle.loads(msg)] = fds[0]
+        sender.join()
+        return got
+
+    def close(self):
+        self.srv.close()
+        if os.path.exists(self.path):
+            os.unlink(self.path)
+
+
 class BgComm:
     """One rank's handle on the peer-memory runtime: arena, groups, collectives.
 
@@ -179,14 +236,18 @@ class BgComm:
     ranks inside this process -- what the single-GPU parity tests use).
     """
 
-    def __init__(self, rank, world, device, arena_bytes):
+    def __init__(self, rank, world, device, arena_bytes, vmm=False):
         import torch
         self.rank, self.world, self.device = int(rank), int(world), int(device)
         self._last_coll, self._coll_events, self._coll_i = None, None, 0
         self._ctx = _vp()
+        self.vmm, self._fd_channel, self._nvls = bool(vmm), None, {}
         torch.cuda.set_device(self.device)
         torch.cuda.init()
-        check(lib().bg_ctx_create(self.rank, self.world, self.device, int(arena_bytes), ctypes.byref(self._ctx)))
+        if vmm:   # arena from the virtual-memory API: what NVSwitch multicast objects can bind (opt-in, HGB_NVLS=1)
+            check(lib().bg_ctx_create_ex(self.rank, self.world, self.device, int(arena_bytes), 1, ctypes.byref(self._ctx)))
+        else:
+            check(lib().bg_ctx_create(self.rank, self.world, self.device, int(arena_bytes), ctypes.byref(self._ctx)))
         base, nbytes, used = _vp(), _sz(), _sz()
         check(lib().bg_arena_info(self._ctx, ctypes.byref(base), ctypes.byref(nbytes), ctypes.byref(used)))
         self.arena_ptr, self.arena_bytes = base.value, nbytes.value
@@ -222,7 +283,79 @@ class BgComm:
                 buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
                 check(lib().bg_arena_import(self._ctx, peer, buf))
 
+    def arena_mode(self):
+        """(vmm arena?, multicast supported?, multicast granularity in bytes)"""
+        v, m, g = _i(), _i(), _sz()
+        check(lib().bg_arena_mode(self._ctx, ctypes.byref(v), ctypes.byref(m), ctypes.byref(g)))
+        return bool(v.value), bool(m.value), int(g.value)
+
+    def connect_vmm(self, pg=None):
+        """``connect_ipc`` for a VMM arena: every rank exports its arena as a file descriptor, sends it to every peer over the
+        unix-socket channel and maps the peers' arenas."""
+        if self.world == 1:
+            return
+        self._fd_channel = _FdChannel(self.rank, self.world, pg)
+        fd = _i()
+        check(lib().bg_arena_export_fd(self._ctx, ctypes.byref(fd)))
+        got = self._fd_channel.exchange([(peer, "arena", fd.value) for peer in range(self.world) if peer != self.rank], self.world - 1)
+        for (src, _tag), pfd in got.items():
+            check(lib().bg_arena_import_fd(self._ctx, src, pfd))
+            os.close(pfd)
+        os.close(fd.value)
+
+    def setup_nvls(self, buffers, pg=None):
+        """Collective over the whole job (every rank calls it once, with ITS buffers): one multicast object per (group,
+        symmetric buffer).  The group's first rank creates the object and hands its descriptor to the members; everybody adds
+        its device; barrier; everybody binds its own arena range; barrier."""
+        import torch.distributed as dist
+        vmm, mc, gran = self.arena_mode()
+        if not (vmm and mc):
+            raise BgError("NVLS needs a VMM arena on a multicast-capable device (arena_mode = %r)" % ((vmm, mc, gran),))
+        outgoing, expected, created = [], 0, {}
+        for buf in buffers:
+            ranks = tuple(buf.group.ranks)
+            gid = self.group_id(buf.group)
+            if buf.offset % gran or buf.nbytes % gran:
+                raise BgError("NVLS buffer of group %s must be aligned to the multicast granularity %d" % (ranks, gran))
+            if self.rank == ranks[0]:
+                fd = _i()
+                check(lib().bg_group_mc_create(self._ctx, gid, int(buf.nbytes), ctypes.byref(fd)))
+                created[ranks] = fd.value
+                outgoing += [(r, ("mc", ranks), fd.value) for r in ranks[1:]]
+            else:
+                expected += 1
+        got = self._fd_channel.exchange(outgoing, expected) if self.world > 1 else {}
+        for buf in buffers:
+            ranks = tuple(buf.group.ranks)
+            gid = self.group_id(buf.group)
+            if self.rank == ranks[0]:
+                check(lib().bg_group_mc_join(self._ctx, gid, -1, int(buf.nbytes)))
+                os.close(created[ranks])
+            else:
+                fd = got[(ranks[0], ("mc", ranks))]
+                check(lib().bg_group_mc_join(self._ctx, gid, fd, int(buf.nbytes)))
+                os.close(fd)
+        if self.world > 1:
+            dist.barrier(group=pg)          # every device is in every object before anyone binds
+        for buf in buffers:
+            check(lib().bg_group_mc_bind(self._ctx, self.group_id(buf.group), int(buf.offset)))
+            self._nvls[tuple(buf.group.ranks)] = buf
+        if self.world > 1:
+            dist.barrier(group=pg)
+
+    def has_nvls(self, group):
+        return tuple(group.ranks) in self._nvls
+
+    def all_reduce_nvls(self, group, byte_offset, dst, elems, dtype, scale=1.0, lane=LANE_ACT, stream=None):
+        """In-switch all-reduce of ``elems`` values at ``byte_offset`` of the group's NVLS buffer -> ``dst`` (or in place)."""
+        with self._in_order(stream) as sp:
+            check(lib().bg_all_reduce_nvls(self._ctx, self.group_id(group), lane, int(byte_offset), _ptr(dst) if dst is not None else None,
+                                           int(elems), dtype_code(dtype), float(scale), sp))
+
     def close(self):
+        if self._fd_channel is not None:
+            self._fd_channel.close()
+            self._fd_channel = None
         if self._ctx:
             self._arena_u8 = None
             check(lib().bg_ctx_destroy(self._ctx))
@@ -245,15 +378,21 @@ class BgComm:
         check(lib().bg_arena_alloc(self._ctx, int(nbytes), ctypes.byref(off)))
         return off.value, self._arena_u8[off.value: off.value + int(nbytes)]
 
-    def sym_alloc(self, group, nbytes, tag=""):
+    def sym_alloc(self, group, nbytes, tag="", align=256):
         """Allocate the calling rank's part of a symmetric buffer.  Members must call this in the same order
-        per group (SPMD); peer offsets become known at the next ``exchange()``."""
-        nbytes = (int(nbytes) + 255) // 256 * 256
+        per group (SPMD); peer offsets become known at the next ``exchange()``.  ``align``: offset AND size granularity
+        (the multicast granularity for a buffer that NVLS binds)."""
+        nbytes = (int(nbytes) + align - 1) // align * align
         ranks = tuple(group.ranks)
         seq = self._sym_seq.get(ranks, 0)
         self._sym_seq[ranks] = seq + 1
         key = (ranks, seq)
-        off, t = self.alloc(nbytes)
+        if align > 256:
+            o = _sz()
+            check(lib().bg_arena_alloc_aligned(self._ctx, nbytes, int(align), ctypes.byref(o)))
+            off, t = o.value, self._arena_u8[o.value: o.value + nbytes]
+        else:
+            off, t = self.alloc(nbytes)
         buf = SymBuffer(self, group, nbytes, off, t, key)
         self._sym[key] = buf
         if group.size > 1:

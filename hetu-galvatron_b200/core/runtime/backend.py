@@ -64,9 +64,14 @@ class CudaBackend:
                     except RuntimeError:
                         arena_bytes = 0
                 arena_bytes = arena_bytes or (1 << 30)
-            comm = _bg.BgComm(self.rank, self.world, self.device_index, arena_bytes)
+            # HGB_NVLS=1 (opt-in): arena from the virtual-memory API so that NVSwitch multicast objects can bind the activation
+            # staging buffers; large tensor-parallel all-reduces then reduce inside the switch
+            self.nvls = os.environ.get("HGB_NVLS", "0") == "1" and self.world > 1
+            comm = _bg.BgComm(self.rank, self.world, self.device_index, arena_bytes, vmm=self.nvls)
             if self.world > 1:
-                comm.connect_ipc()
+                comm.connect_vmm() if self.nvls else comm.connect_ipc()
+            if self.nvls and not comm.arena_mode()[1]:
+                self.nvls = False          # no multicast on this device / fabric: peer-to-peer kernels only
         self.comm = comm
         if os.environ.get("HGB_TIMEOUT_MS"):      # device-side barrier timeout (default 60 s): shorter for debugging runs
             _bg.set_tunable("timeout_ms", int(os.environ["HGB_TIMEOUT_MS"]))
@@ -89,8 +94,12 @@ class CudaBackend:
     def sym_alloc(self, group, nbytes):
         return self.comm.sym_alloc(group, nbytes)
 
+    NVLS_MIN_BYTES = 1 << 20     # below this the one-shot / two-shot peer kernels win (latency)
+
     def exchange(self):
         self.comm.exchange()
+        if getattr(self, "nvls", False) and self._staging:
+            self.comm.setup_nvls([buf for buf in self._staging.values() if buf.group.size > 1])
 
     def reserve_staging(self, group, nbytes):
         """Per-group activation staging buffer (peer-visible).  Must be called (identically on all members) before
@@ -103,7 +112,8 @@ class CudaBackend:
         if cur is None or cur.data_bytes < nbytes:
             if cur is not None and cur.offsets is not None:
                 raise self.bg.BgError("staging buffer for group %s is %d B, need %d B (reserve before exchange())" % (key, cur.data_bytes, nbytes))
-            buf = self.comm.sym_alloc(group, nbytes + self.FLAG_BYTES)   # tail: per-tile arrival counters of the fused GEMM+RS
+            align = self.comm.arena_mode()[2] if getattr(self, "nvls", False) else 256
+            buf = self.comm.sym_alloc(group, nbytes + self.FLAG_BYTES, align=max(256, align))   # tail: per-tile arrival counters of the fused GEMM+RS
             buf.data_bytes = nbytes
             buf.u8[nbytes:].zero_()
             self._staging[key] = buf
@@ -254,6 +264,11 @@ class CudaBackend:
             return out
         buf, off = self._stage(x, group)
         out = torch.empty_like(x)
+        nbytes = x.numel() * x.element_size()
+        if (getattr(self, "nvls", False) and op == "sum" and nbytes >= self.NVLS_MIN_BYTES and self.comm.has_nvls(group)
+                and x.dtype in (torch.bfloat16, torch.float32)):
+            self.comm.all_reduce_nvls(group, off, out, x.numel(), x.dtype)       # reduced and replicated inside the NVSwitch
+            return out
         self.comm.all_reduce(group, buf, out, elems=x.numel(), op=self.bg.MAX if op == "max" else self.bg.SUM,
                              src_byte_offset=off)
         return out

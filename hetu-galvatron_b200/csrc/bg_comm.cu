@@ -9,6 +9,8 @@
 #include <tuple>
 #include <vector>
 
+#include <cuda.h>
+
 #include "bg_common.cuh"
 
 namespace bg {
@@ -50,6 +52,19 @@ struct bg_ctx {
     int* err_dev = nullptr;
     unsigned long long p2p_sent[BG_MAX_WORLD][64] = {};
     std::mutex mu;
+    // ---- VMM arena / NVLS multicast (opt-in) ----
+    bool vmm = false;
+    int mc_supported = 0;
+    size_t vmm_gran = 0, mc_gran = 0;
+    CUmemGenericAllocationHandle arena_handle = 0;
+    CUmemGenericAllocationHandle peer_handle[BG_MAX_WORLD] = {};
+    struct McGroup {
+        CUmemGenericAllocationHandle mc = 0;
+        CUdeviceptr va = 0;
+        size_t bytes = 0, arena_off = 0;
+        bool bound = false;
+    };
+    std::map<int, McGroup> mc_of;   // gid -> multicast object over the group's NVLS buffer
 };
 
 // signal pad: pad[slot][lane][channel][BG_MAX_PEERS] u32, followed by the p2p flags [BG_MAX_WORLD][P2P_FLAGS]
@@ -64,6 +79,112 @@ static void enumerate_slots(bg_ctx* c) {
             for (int first = 0; first + (size - 1) * stride < c->world; ++first)
                 c->slot_of[std::make_tuple(first, stride, size)] = next++;
 }
+
+
+// =================================================================================================================
+// VMM arena + NVLS (NVSwitch multicast) all-reduce.  OPT-IN (bg_ctx_create_ex flag BG_CTX_VMM, HGB_NVLS=1 on the host side):
+// the default arena is cudaMalloc + cudaIpc.  Multicast objects can only bind memory that was created with cuMemCreate, so
+// this mode allocates the arena through the virtual-memory API and shares it (and the multicast objects) between the
+// processes as POSIX file descriptors, which the host passes over a unix socket (SCM_RIGHTS).
+// Replaces NCCL's NVLS all-reduce for the tensor-parallel reductions (mappings_group.py:19, layers.py:474-480):
+// two-shot -- every member reduces ITS slice in the switch (multimem.ld_reduce) and broadcasts it (multimem.st).
+// =================================================================================================================
+
+namespace {
+
+struct Drv {
+    CUresult (*MemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*MemRelease)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*MemAddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*MemAddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*MemExportToShareableHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+    CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType) = nullptr;
+    CUresult (*MemGetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*MulticastCreate)(CUmemGenericAllocationHandle*, const CUmulticastObjectProp*) = nullptr;
+    CUresult (*MulticastAddDevice)(CUmemGenericAllocationHandle, CUdevice) = nullptr;
+    CUresult (*MulticastBindMem)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long) = nullptr;
+    CUresult (*MulticastGetGranularity)(size_t*, const CUmulticastObjectProp*, CUmulticastGranularity_flags) = nullptr;
+    CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
+    CUresult (*DeviceGetAttribute)(int*, CUdevice_attribute, CUdevice) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    bool ok = false;
+};
+
+template <typename F>
+bool drv_sym(const char* name, F* out) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+        cudaGetLastError();
+        return false;
+    }
+    *out = reinterpret_cast<F>(p);
+    return true;
+}
+
+Drv& drv() {
+    static Drv d;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        bool ok = true;
+        ok &= drv_sym("cuMemCreate", &d.MemCreate);
+        ok &= drv_sym("cuMemRelease", &d.MemRelease);
+        ok &= drv_sym("cuMemAddressReserve", &d.MemAddressReserve);
+        ok &= drv_sym("cuMemAddressFree", &d.MemAddressFree);
+        ok &= drv_sym("cuMemMap", &d.MemMap);
+        ok &= drv_sym("cuMemUnmap", &d.MemUnmap);
+        ok &= drv_sym("cuMemSetAccess", &d.MemSetAccess);
+        ok &= drv_sym("cuMemExportToShareableHandle", &d.MemExportToShareableHandle);
+        ok &= drv_sym("cuMemImportFromShareableHandle", &d.MemImportFromShareableHandle);
+        ok &= drv_sym("cuMemGetAllocationGranularity", &d.MemGetAllocationGranularity);
+        ok &= drv_sym("cuMulticastCreate", &d.MulticastCreate);
+        ok &= drv_sym("cuMulticastAddDevice", &d.MulticastAddDevice);
+        ok &= drv_sym("cuMulticastBindMem", &d.MulticastBindMem);
+        ok &= drv_sym("cuMulticastGetGranularity", &d.MulticastGetGranularity);
+        ok &= drv_sym("cuDeviceGet", &d.DeviceGet);
+        ok &= drv_sym("cuDeviceGetAttribute", &d.DeviceGetAttribute);
+        ok &= drv_sym("cuGetErrorString", &d.GetErrorString);
+        d.ok = ok;
+    });
+    return d;
+}
+
+int drv_fail(const char* what, CUresult r) {
+    const char* msg = nullptr;
+    if (drv().GetErrorString) drv().GetErrorString(r, &msg);
+    return fail(BG_ECUDA, "%s: %s (CUresult %d)", what, msg ? msg : "?", (int)r);
+}
+#define BG_DRV(expr)                                   \
+    do {                                               \
+        CUresult _r = (expr);                          \
+        if (_r != CUDA_SUCCESS) return drv_fail(#expr, _r); \
+    } while (0)
+
+CUmemAllocationProp arena_prop(int device) {
+    CUmemAllocationProp prop = {};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    return prop;
+}
+
+int map_rw(CUdeviceptr* va, size_t bytes, size_t align, CUmemGenericAllocationHandle h, int device) {
+    Drv& d = drv();
+    BG_DRV(d.MemAddressReserve(va, bytes, align, 0, 0));
+    BG_DRV(d.MemMap(*va, bytes, 0, h, 0));
+    CUmemAccessDesc acc = {};
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = device;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    BG_DRV(d.MemSetAccess(*va, bytes, &acc, 1));
+    return BG_OK;
+}
+
+}  // namespace
 
 extern "C" int bg_abi_version(void) { return BG_ABI_VERSION; }
 extern "C" const char* bg_last_error(void) { return g_last_error.c_str(); }
@@ -91,10 +212,11 @@ extern "C" long long bg_get_tunable(const char* name) {
     return t ? *t : -1;
 }
 
-extern "C" int bg_ctx_create(int rank, int world, int device, size_t arena_bytes, bg_ctx_t* out) {
+extern "C" int bg_ctx_create_ex(int rank, int world, int device, size_t arena_bytes, unsigned flags, bg_ctx_t* out) {
     if (!out || world < 1 || world > BG_MAX_WORLD || rank < 0 || rank >= world)
         return fail(BG_EINVAL, "bg_ctx_create: bad rank/world %d/%d", rank, world);
     BG_CUDA(cudaSetDevice(device));
+    BG_CUDA(cudaFree(0));   // the primary context exists before any driver-API call
     bg_ctx* c = new bg_ctx();
     c->rank = rank; c->world = world; c->device = device;
     memset(c->peer_base, 0, sizeof(c->peer_base));
@@ -104,11 +226,48 @@ extern "C" int bg_ctx_create(int rank, int world, int device, size_t arena_bytes
     pad = (pad + 4095) / 4096 * 4096;
     c->pad_bytes = pad;
     c->arena_bytes = pad + ((arena_bytes + 4095) / 4096 * 4096);
-    cudaError_t e = cudaMalloc(&c->arena, c->arena_bytes);
-    if (e != cudaSuccess) {
-        size_t want = c->arena_bytes;
-        delete c;
-        return fail(BG_ENOMEM, "arena cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+    if (flags & BG_CTX_VMM) {
+        Drv& d = drv();
+        int rc = BG_OK;
+        if (!d.ok) rc = fail(BG_ECUDA, "the driver does not expose the virtual-memory / multicast entry points");
+        CUmemAllocationProp prop = arena_prop(device);
+        size_t gran = 0;
+        CUdevice dev = 0;
+        if (!rc && d.MemGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS)
+            rc = fail(BG_ECUDA, "cuMemGetAllocationGranularity failed");
+        if (!rc && d.DeviceGet(&dev, device) == CUDA_SUCCESS)
+            d.DeviceGetAttribute(&c->mc_supported, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev);
+        if (!rc && c->mc_supported) {
+            CUmulticastObjectProp mp = {};
+            mp.numDevices = world > 1 ? (unsigned)world : 2u;
+            mp.size = gran;
+            mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+            size_t mg = 0;
+            if (d.MulticastGetGranularity(&mg, &mp, CU_MULTICAST_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS && mg) {
+                c->mc_gran = mg;
+                if (mg > gran) gran = mg;
+            } else {
+                c->mc_supported = 0;
+            }
+        }
+        if (!rc) {
+            c->vmm = true;
+            c->vmm_gran = gran;
+            c->arena_bytes = (c->arena_bytes + gran - 1) / gran * gran;
+            CUresult r = d.MemCreate(&c->arena_handle, c->arena_bytes, &prop, 0);
+            if (r != CUDA_SUCCESS) rc = drv_fail("cuMemCreate(arena)", r);
+        }
+        CUdeviceptr va = 0;
+        if (!rc) rc = map_rw(&va, c->arena_bytes, c->vmm_gran, c->arena_handle, device);
+        if (rc) { delete c; return rc; }
+        c->arena = (char*)va;
+    } else {
+        cudaError_t e = cudaMalloc(&c->arena, c->arena_bytes);
+        if (e != cudaSuccess) {
+            size_t want = c->arena_bytes;
+            delete c;
+            return fail(BG_ENOMEM, "arena cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+        }
     }
     BG_CUDA(cudaMemset(c->arena, 0, pad));
     BG_CUDA(cudaHostAlloc(&c->err_host, 8 * sizeof(int), cudaHostAllocMapped));   // [0] status, [1..7] who/where
@@ -121,13 +280,33 @@ extern "C" int bg_ctx_create(int rank, int world, int device, size_t arena_bytes
     return BG_OK;
 }
 
+extern "C" int bg_ctx_create(int rank, int world, int device, size_t arena_bytes, bg_ctx_t* out) {
+    return bg_ctx_create_ex(rank, world, device, arena_bytes, 0u, out);
+}
+
 extern "C" int bg_ctx_destroy(bg_ctx_t c) {
     if (!c) return BG_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (int r = 0; r < c->world; ++r)
-        if (c->peer_ipc[r] && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
-    if (c->arena) cudaFree(c->arena);
+    if (c->vmm) {
+        Drv& d = drv();
+        for (auto& kv : c->mc_of) {
+            if (kv.second.va) { d.MemUnmap(kv.second.va, kv.second.bytes); d.MemAddressFree(kv.second.va, kv.second.bytes); }
+            if (kv.second.mc) d.MemRelease(kv.second.mc);
+        }
+        for (int r = 0; r < c->world; ++r)
+            if (r != c->rank && c->peer_handle[r]) {
+                d.MemUnmap((CUdeviceptr)c->peer_base[r], c->arena_bytes);
+                d.MemAddressFree((CUdeviceptr)c->peer_base[r], c->arena_bytes);
+                d.MemRelease(c->peer_handle[r]);
+            }
+        if (c->arena) { d.MemUnmap((CUdeviceptr)c->arena, c->arena_bytes); d.MemAddressFree((CUdeviceptr)c->arena, c->arena_bytes); }
+        if (c->arena_handle) d.MemRelease(c->arena_handle);
+    } else {
+        for (int r = 0; r < c->world; ++r)
+            if (c->peer_ipc[r] && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+        if (c->arena) cudaFree(c->arena);
+    }
     if (c->err_host) cudaFreeHost(c->err_host);
     delete c;
     return BG_OK;
@@ -152,8 +331,50 @@ extern "C" int bg_arena_alloc(bg_ctx_t c, size_t bytes, size_t* offset) {
     return BG_OK;
 }
 
+extern "C" int bg_arena_alloc_aligned(bg_ctx_t c, size_t bytes, size_t align, size_t* offset) {
+    if (!c || !offset || !align) return fail(BG_EINVAL, "null arg");
+    std::lock_guard<std::mutex> lk(c->mu);
+    size_t off = (c->bump + align - 1) / align * align;
+    if (off + bytes > c->arena_bytes)
+        return fail(BG_ENOMEM, "arena exhausted: want %zu at %zu of %zu (raise arena_bytes)", bytes, off, c->arena_bytes);
+    c->bump = off + bytes;
+    *offset = off;
+    return BG_OK;
+}
+
+extern "C" int bg_arena_mode(bg_ctx_t c, int* vmm, int* multicast, size_t* mc_granularity) {
+    if (!c) return fail(BG_EINVAL, "null ctx");
+    if (vmm) *vmm = c->vmm ? 1 : 0;
+    if (multicast) *multicast = c->vmm ? c->mc_supported : 0;
+    if (mc_granularity) *mc_granularity = c->mc_gran;
+    return BG_OK;
+}
+
+extern "C" int bg_arena_export_fd(bg_ctx_t c, int* fd) {
+    if (!c || !fd) return fail(BG_EINVAL, "null arg");
+    if (!c->vmm) return fail(BG_EINVAL, "bg_arena_export_fd needs a BG_CTX_VMM context (cudaMalloc arenas use bg_arena_export)");
+    BG_CUDA(cudaSetDevice(c->device));
+    BG_DRV(drv().MemExportToShareableHandle(fd, c->arena_handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+    return BG_OK;
+}
+
+extern "C" int bg_arena_import_fd(bg_ctx_t c, int peer, int fd) {
+    if (!c || peer < 0 || peer >= c->world || fd < 0) return fail(BG_EINVAL, "bad peer %d / fd %d", peer, fd);
+    if (!c->vmm) return fail(BG_EINVAL, "bg_arena_import_fd needs a BG_CTX_VMM context");
+    if (peer == c->rank) return BG_OK;
+    BG_CUDA(cudaSetDevice(c->device));
+    Drv& d = drv();
+    BG_DRV(d.MemImportFromShareableHandle(&c->peer_handle[peer], (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+    CUdeviceptr va = 0;
+    int rc = map_rw(&va, c->arena_bytes, c->vmm_gran, c->peer_handle[peer], c->device);   // every rank's arena has the same size
+    if (rc) return rc;
+    c->peer_base[peer] = (char*)va;
+    return BG_OK;
+}
+
 extern "C" int bg_arena_export(bg_ctx_t c, void* handle64) {
     if (!c || !handle64) return fail(BG_EINVAL, "null arg");
+    if (c->vmm) return fail(BG_EINVAL, "a BG_CTX_VMM arena is shared with bg_arena_export_fd");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
     BG_CUDA(cudaSetDevice(c->device));
     BG_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, c->arena));
@@ -1025,4 +1246,157 @@ extern "C" int bg_gemm_reduce_scatter(bg_ctx_t c, int gid, int lane, const void*
     for (int i = 0; i < BG_MAX_PEERS; ++i) { pp[i] = partial.p[i]; fp[i] = (uint32_t*)flags.p[i]; }
     return bg_gemm_scatter_launch(a, b, m, n, k, layout, g->n, g->me, pp, fp, out, (unsigned long long)g_tun.timeout_ms * 1000000ull,
                                   c->err_dev, st);
+}
+
+// ---- NVLS: multicast object over one group's symmetric buffer ---------------------------------------------------------
+static int mc_group(bg_ctx* c, int gid, const Group** gout) {
+    if (!c) return fail(BG_EINVAL, "null ctx");
+    if (gid < 0 || gid >= (int)c->groups.size()) return fail(BG_EGROUP, "bad gid %d", gid);
+    if (!c->vmm || !c->mc_supported) return fail(BG_EINVAL, "NVLS needs a BG_CTX_VMM context on a multicast-capable device");
+    *gout = &c->groups[gid];
+    if ((*gout)->n < 2) return fail(BG_EINVAL, "NVLS needs a group of >= 2 ranks");
+    return BG_OK;
+}
+
+extern "C" int bg_group_mc_create(bg_ctx_t c, int gid, size_t bytes, int* fd_out) {
+    const Group* g;
+    int rc = mc_group(c, gid, &g);
+    if (rc) return rc;
+    if (!fd_out || !bytes) return fail(BG_EINVAL, "null arg");
+    BG_CUDA(cudaSetDevice(c->device));
+    bg_ctx::McGroup& m = c->mc_of[gid];
+    if (m.mc) return fail(BG_EINVAL, "group %d already has a multicast object", gid);
+    CUmulticastObjectProp mp = {};
+    mp.numDevices = (unsigned)g->n;
+    mp.size = (bytes + c->mc_gran - 1) / c->mc_gran * c->mc_gran;
+    mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    BG_DRV(drv().MulticastCreate(&m.mc, &mp));
+    m.bytes = mp.size;
+    BG_DRV(drv().MemExportToShareableHandle(fd_out, m.mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+    return BG_OK;
+}
+
+// fd >= 0: import the creator's object (every other member); then add this rank's device.  ALL members must have joined
+// before any of them binds (host-side barrier).
+extern "C" int bg_group_mc_join(bg_ctx_t c, int gid, int fd, size_t bytes) {
+    const Group* g;
+    int rc = mc_group(c, gid, &g);
+    if (rc) return rc;
+    BG_CUDA(cudaSetDevice(c->device));
+    bg_ctx::McGroup& m = c->mc_of[gid];
+    if (fd >= 0) {
+        if (m.mc) return fail(BG_EINVAL, "group %d already has a multicast object", gid);
+        BG_DRV(drv().MemImportFromShareableHandle(&m.mc, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+        m.bytes = (bytes + c->mc_gran - 1) / c->mc_gran * c->mc_gran;
+    }
+    if (!m.mc) return fail(BG_EINVAL, "group %d has no multicast object (create or import first)", gid);
+    CUdevice dev = 0;
+    BG_DRV(drv().DeviceGet(&dev, c->device));
+    BG_DRV(drv().MulticastAddDevice(m.mc, dev));
+    return BG_OK;
+}
+
+extern "C" int bg_group_mc_bind(bg_ctx_t c, int gid, size_t arena_offset) {
+    const Group* g;
+    int rc = mc_group(c, gid, &g);
+    if (rc) return rc;
+    BG_CUDA(cudaSetDevice(c->device));
+    bg_ctx::McGroup& m = c->mc_of[gid];
+    if (!m.mc || m.bound) return fail(BG_EINVAL, "group %d: multicast object missing or already bound", gid);
+    if (arena_offset % c->mc_gran || arena_offset < c->pad_bytes || arena_offset + m.bytes > c->arena_bytes)
+        return fail(BG_EINVAL, "NVLS buffer [%zu,+%zu) must be multicast-granularity (%zu) aligned inside the arena", arena_offset, m.bytes,
+                    c->mc_gran);
+    BG_DRV(drv().MulticastBindMem(m.mc, 0, c->arena_handle, arena_offset, m.bytes, 0));
+    rc = map_rw(&m.va, m.bytes, c->mc_gran, m.mc, c->device);
+    if (rc) return rc;
+    m.arena_off = arena_offset;
+    m.bound = true;
+    return BG_OK;
+}
+
+namespace {
+
+__device__ __forceinline__ uint4 mm_ld_reduce_bf16(const void* mc) {   // sum over every member's copy, fp32 accumulation in the switch
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 mm_ld_reduce_f32(const void* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mm_st_16(void* mc, const uint4& v) {    // one store, lands in every member's copy
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
+}
+
+// Two-shot all-reduce through the switch, in place on the group's multicast-bound buffer, then a local copy to dst.
+//   phase 1: member r owns vectors [r*per, (r+1)*per): ld_reduce pulls the SUM of all members' values (one NVLink read of the
+//            reduced data instead of p-1 reads), scale, multimem.st pushes the result into every member's buffer
+//   phase 2: after the barrier every member's buffer holds the full result; copy it out (local HBM)
+// NVLink bytes per GPU: N/p received + N/p sent through the switch's reduction / replication, vs 2(p-1)/p*N for the P2P two-shot.
+template <bool kBf16>
+__global__ void __launch_bounds__(256, 2) all_reduce_nvls_kernel(char* mc, const char* local, char* dst, size_t vecs, float scale,
+                                                                Sig s) {
+    sync_peers<false, false, true>(s);   // every member's input is complete (its producers precede this kernel in its stream)
+    const size_t per = (vecs + s.n - 1) / s.n;
+    const size_t lo = per * s.me, hi = lo + per < vecs ? lo + per : vecs;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t v = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < hi; v += stride) {
+        uint4 out;
+        if (kBf16) {
+            uint4 in = mm_ld_reduce_bf16(mc + v * 16);
+            if (scale != 1.0f) {
+                float f[8];
+                unpack8(in, f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] *= scale;
+                in = pack8(f);
+            }
+            out = in;
+        } else {
+            float4 in = mm_ld_reduce_f32(mc + v * 16);
+            out.x = __float_as_uint(in.x * scale); out.y = __float_as_uint(in.y * scale);
+            out.z = __float_as_uint(in.z * scale); out.w = __float_as_uint(in.w * scale);
+        }
+        mm_st_16(mc + v * 16, out);
+    }
+    sync_peers<true, true, true>(s);     // my stores are visible everywhere and everyone's slice has landed here
+    if (dst != nullptr) {
+        for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < vecs; v += stride)
+            st16(dst + v * 16, ld16_stream(local + v * 16));
+        // the buffer may be refilled by the next call's producers only after every member has finished reading it: the next
+        // call's entry barrier cannot give that (it waits for producers, not consumers), so leave through a barrier
+        sync_peers<true, false, false>(s);
+    }
+}
+
+}  // namespace
+
+extern "C" int bg_all_reduce_nvls(bg_ctx_t c, int gid, int lane, size_t byte_offset, void* dst, size_t elems, int dtype, float scale,
+                                  void* stream) {
+    Sig s; const Group* g;
+    int rc = make_sig(c, gid, lane, &s, &g);
+    if (rc) return rc;
+    auto it = c->mc_of.find(gid);
+    if (it == c->mc_of.end() || !it->second.bound) return fail(BG_EINVAL, "group %d has no bound NVLS buffer", gid);
+    const bg_ctx::McGroup& m = it->second;
+    const size_t esz = dtype == BG_BF16 ? 2 : dtype == BG_F32 ? 4 : 0;
+    if (!esz) return fail(BG_EUNSUPPORTED, "bg_all_reduce_nvls: bf16 or fp32");
+    if (elems * esz % 16) return fail(BG_EINVAL, "bg_all_reduce_nvls: payload must be a multiple of 16 bytes");
+    if (byte_offset % 16 || byte_offset + elems * esz > m.bytes)
+        return fail(BG_EINVAL, "bg_all_reduce_nvls: [%zu,+%zu) outside the bound buffer (%zu B) or misaligned", byte_offset, elems * esz, m.bytes);
+    BG_CUDA(cudaSetDevice(c->device));
+    const size_t vecs = elems * esz / 16;
+    const int grid = comm_grid((vecs + g->n - 1) / g->n, 256, g->n);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == BG_BF16)
+        all_reduce_nvls_kernel<true><<<grid, 256, 0, st>>>((char*)m.va + byte_offset, c->arena + m.arena_off + byte_offset, (char*)dst, vecs, scale, s);
+    else
+        all_reduce_nvls_kernel<false><<<grid, 256, 0, st>>>((char*)m.va + byte_offset, c->arena + m.arena_off + byte_offset, (char*)dst, vecs, scale, s);
+    BG_CHECK_LAUNCH();
+    return BG_OK;
 }

@@ -52,12 +52,21 @@ unsigned long long bg_launch_count(void);
 
 /* ---- context + symmetric arena (replaces ProcessGroupNCCL communicator state) --------------------------- */
 int bg_ctx_create(int rank, int world, int device, size_t arena_bytes, bg_ctx_t* out);
+/* flags: BG_CTX_VMM allocates the arena with the virtual-memory API (cuMemCreate) instead of cudaMalloc; that is what NVSwitch
+ * multicast objects can bind.  Such an arena is shared between processes as a POSIX file descriptor (bg_arena_export_fd /
+ * bg_arena_import_fd; the host passes the descriptor over a unix socket) instead of a cudaIpc handle.  OPT-IN. */
+#define BG_CTX_VMM 1u
+int bg_ctx_create_ex(int rank, int world, int device, size_t arena_bytes, unsigned flags, bg_ctx_t* out);
 int bg_ctx_destroy(bg_ctx_t ctx);
 int bg_arena_info(bg_ctx_t ctx, void** base, size_t* bytes, size_t* used);
 int bg_arena_alloc(bg_ctx_t ctx, size_t bytes, size_t* offset);        /* 256-B aligned bump allocation */
 int bg_arena_export(bg_ctx_t ctx, void* handle64);                      /* cudaIpcMemHandle_t, 64 bytes */
 int bg_arena_import(bg_ctx_t ctx, int peer_rank, const void* handle64); /* map a peer process's arena */
 int bg_arena_attach_local(bg_ctx_t ctx, int peer_rank, bg_ctx_t peer);  /* peer ctx in this process */
+int bg_arena_alloc_aligned(bg_ctx_t ctx, size_t bytes, size_t align, size_t* offset);
+int bg_arena_mode(bg_ctx_t ctx, int* vmm, int* multicast_supported, size_t* multicast_granularity);
+int bg_arena_export_fd(bg_ctx_t ctx, int* fd);                          /* BG_CTX_VMM arenas */
+int bg_arena_import_fd(bg_ctx_t ctx, int peer_rank, int fd);
 int bg_ctx_error_flag(bg_ctx_t ctx, int* flag);                         /* device-side timeout report */
 /* info8[0] = status; [1] = kind (1 signalling a peer, 2 waiting for a peer, 3 fused-GEMM tile reducer);
  * [2] = CTA; [3] = thread or tile; [4] = value last seen; [5], [6] = group index/size or expected count/tiles.
@@ -174,6 +183,18 @@ int bg_gemm_bf16(const void* a, const void* b, void* c, long long m, long long n
  * zero-initialised.  M must be a multiple of p*128.  `out` is complete in stream order. */
 int bg_gemm_reduce_scatter(bg_ctx_t ctx, int gid, int lane, const void* a, const void* b, long long m, long long n, long long k,
                            int layout, const size_t* partial_offs, const size_t* flag_offs, void* out, void* stream);
+
+/* ---- NVLS: all-reduce reduced and replicated INSIDE the NVSwitch (multimem.ld_reduce / multimem.st) ---------------------
+ * Replaces the tensor-parallel all-reduces (mappings_group.py:19, layers.py:474-480) for large messages, where NCCL itself
+ * switches to NVLS: N/p bytes in and N/p out per GPU instead of 2(p-1)/p*N.  One multicast object per group over one
+ * symmetric buffer: the group's first rank creates it (-> fd), every other member imports the fd, ALL join (device added),
+ * barrier on the host, ALL bind their own arena range (multicast-granularity aligned), then bg_all_reduce_nvls works in
+ * place on that buffer and copies the result to dst (dst may be NULL: result left in the buffer).  BG_CTX_VMM contexts only. */
+int bg_group_mc_create(bg_ctx_t ctx, int gid, size_t bytes, int* fd_out);
+int bg_group_mc_join(bg_ctx_t ctx, int gid, int fd /* -1 on the creator */, size_t bytes);
+int bg_group_mc_bind(bg_ctx_t ctx, int gid, size_t arena_offset);
+int bg_all_reduce_nvls(bg_ctx_t ctx, int gid, int lane, size_t byte_offset, void* dst, size_t elems, int dtype, float scale,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -86,3 +86,16 @@ def test_checkpoint_load_save_resume(world, name, tmp_path):
     assert abs(a["losses"][0] - EXPECTED["hf_loss_fp32"]) <= 5e-3 * EXPECTED["hf_loss_fp32"]
     b = launch(world, dict(over, load=out, distributed_checkpoint=True, load_iteration=2, _skip_batches=2, _iters=1), backend="cuda")
     assert abs(b["losses"][0] - a["losses"][2]) <= 1e-6 * abs(a["losses"][2]), (a["losses"], b["losses"], json.dumps(over))
+
+
+@pytest.mark.parametrize("n", [2, 8])
+def test_nvls_all_reduce(n):
+    """Opt-in VMM arena + in-switch (multimem) all-reduce against NCCL; a box without NVSwitch multicast must still run the
+    ordinary peer kernels on the VMM arena (NVLS_UNSUPPORTED)."""
+    _need(n)
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
+                          "127.0.0.1", "--master-port", str(29850 + n), os.path.join(root, "scripts", "test_nvls.py")],
+                         capture_output=True, text=True, timeout=600, env=dict(os.environ, NVLS_MAX_MB="256"))
+    assert out.returncode == 0 and ("NVLS_OK" in out.stdout or "NVLS_UNSUPPORTED" in out.stdout), out.stdout[-3000:] + out.stderr[-3000:]
