@@ -121,6 +121,11 @@ def construct_hybrid_parallel_model_api(model, model_config, training_args, hybr
         raise ValueError("this strategy mixes Ulysses layers (use_sp=1) with tensor-parallel / data-parallel rows: "
                          "it needs --sequence-parallel (activations must be sequence-split on both sides of a relocation)")
 
+    cp_rows = set(hp_whole["cp_sizes_whole"])
+    if len(cp_rows) > 1 and not args.sequence_parallel:
+        raise ValueError("this strategy changes the context-parallel degree between rows: it needs --sequence-parallel "
+                         "(the relocation re-splits the sequence only under that flag, redistribute.py:60,121)")
+
     # [Step 0] communication groups (pure rank lists)
     (pp_group, tp_groups_whole, sp_groups_whole, cp_groups_whole, dp_groups_whole, seq_data_groups_whole,
      allgather_tp_sp_groups_whole, split_tp_sp_groups_whole, allgather_cp_groups_whole, split_cp_groups_whole,

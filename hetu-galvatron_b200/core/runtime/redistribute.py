@@ -85,7 +85,13 @@ def _relocate_float(x, allgather_cp_group, allgather_sep_group, split_cp_group, 
                     fused_split_group, sequence_parallel, sbh):
     if sequence_parallel and _size(split_sep_group) > 1:
         x = _gather_first_dim(x, split_sep_group)
-    old_cp, new_cp = _size(split_cp_group), _size(allgather_cp_group)
+    # Reference quirk g1: gen_redistributed_group_with_cp returns (tp_old, tp_new, cp_new, cp_old) but is unpacked as
+    # (split_tp_sp, allgather_tp_sp, split_cp, allgather_cp) (comm_groups.py:306 vs :483), so ``split_cp_group`` is the NEW layer's
+    # context-parallel group and ``allgather_cp_group`` the OLD one.  The mapping is kept bit-exact (goldens); the reference then
+    # reads the sizes the other way round (redistribute.py:290-296) and applies the wrong token permutation whenever the cp
+    # degree changes between two rows.  Here the sizes are read for what the slots actually hold, which makes mixed-cp
+    # strategies numerically correct (tests: cp_mixed_* in tests/test_host_runtime.py).
+    old_cp, new_cp = _size(allgather_cp_group), _size(split_cp_group)
     if old_cp != new_cp:
         x = _reverse_zigzag_transformation(x, old_cp)
         x = _zigzag_transformation(x, new_cp)

@@ -48,6 +48,11 @@ WORLD2 = {
     "tp2": dict(global_tp_deg=2, vocab_tp=2),
     # context parallelism: zigzag token chunks, keys/values gathered over the cp group, per-chunk causal attention
     "cp2": dict(global_cp_deg=2, vocab_cp=2),
+    # the cp degree changes between rows (embedding / head cp 1, layers cp 2): relocation re-zigzags the sequence.  The
+    # reference applies the wrong permutation here (first row); this runtime reads the group slots for what they hold
+    "cp_mixed_vcp1_layers_cp2": dict(sequence_parallel=True, _strategy_json={
+        "pp_deg": 1, "tp_sizes_enc": "1,1", "tp_consecutive_flags": "1,1", "dp_types_enc": "0,0", "use_sp": "0,0", "cp_sizes_enc": "2,2",
+        "checkpoint": "0,0", "global_bsz": 4, "chunks": 1, "default_dp_type": "zero2", "vtp": 1, "vsp": 0, "vcp": 1}),
     "tp2_megatron_sp": dict(global_tp_deg=2, vocab_tp=2, sequence_parallel=True),
     # shapes the fused GEMM+reduce-scatter accepts (M = 256 = p x 128): on the GPU the row-parallel forward and the
     # column-parallel dgrad run as ONE kernel pair inside the model (forced: these K are below the profitability threshold)
@@ -73,6 +78,12 @@ WORLD4 = {
     # BASELINE config (5) shape: ZeRO-3 on every layer + activation checkpointing
     "baseline5_zero3_ckpt_dp4": dict(sdp=1, global_checkpoint=1, embed_sdp=1, chunks=1, global_train_batch_size=8),
     "cp2_dp2_zero3_ckpt": dict(global_cp_deg=2, vocab_cp=2, sdp=1, global_checkpoint=1, chunks=2, global_train_batch_size=8),
+    "cp_mixed_tp2_to_cp2": dict(sequence_parallel=True, _strategy_json={
+        "pp_deg": 1, "tp_sizes_enc": "2,1", "tp_consecutive_flags": "1,1", "dp_types_enc": "0,1", "use_sp": "0,0", "cp_sizes_enc": "1,2",
+        "checkpoint": "0,1", "global_bsz": 4, "chunks": 2, "default_dp_type": "zero2", "vtp": 2, "vsp": 0, "vcp": 1}),
+    "cp_mixed_cp4_to_tp2cp2": dict(sequence_parallel=True, _strategy_json={
+        "pp_deg": 1, "tp_sizes_enc": "1,2", "tp_consecutive_flags": "1,1", "dp_types_enc": "0,0", "use_sp": "0,0", "cp_sizes_enc": "4,2",
+        "checkpoint": "0,0", "global_bsz": 4, "chunks": 1, "default_dp_type": "zero2", "vtp": 1, "vsp": 0, "vcp": 2}),
     "cp2_pp2_1f1b": dict(global_cp_deg=2, vocab_cp=2, pp_deg=2, chunks=2, pipeline_type="pipedream_flush"),
     "cp2_tp2_megatron_sp": dict(global_cp_deg=2, vocab_cp=2, global_tp_deg=2, vocab_tp=2, sequence_parallel=True),
     "hybrid_mixed": dict(sequence_parallel=True, _spec={"n_kv_heads": 4},
