@@ -107,6 +107,9 @@ WORLD8 = {
                                                                   chunks=2, pp_division="4", vtp=4, vsp=1)),
     "ref_hybrid2_pp2_vtp2": dict(_spec=_SPEC8, sequence_parallel=True, _strategy_json=dict(_HYBRID, pp_deg=2, tp_sizes_enc="1,2,4,2", dp_types_enc="0,1,0,1",
                                                                   chunks=2, pp_division="3,1", vtp=2, vsp=0)),
+    # TP2 x CP2 x DP2 (the SURVEY 8c known-answer mapping: tp {0,1}.. cp {0,2}.. dp {0,4}.. sdp {0,2,4,6}..), ZeRO-3 + checkpointing
+    "tp2_cp2_dp2_zero3": dict(_spec=_SPEC8, sequence_parallel=True, global_tp_deg=2, vocab_tp=2, global_cp_deg=2, vocab_cp=2, sdp=1,
+                              global_checkpoint=1, chunks=2, global_train_batch_size=8),
     "ref_hybrid3_pp2_vsp4": dict(_spec=_SPEC8, sequence_parallel=True, _strategy_json=dict(_HYBRID, pp_deg=2, tp_sizes_enc="1,2,4,2", dp_types_enc="1,0,1,0",
                                                                   chunks=4, pp_division="2,2", vtp=4, vsp=1)),
 }
