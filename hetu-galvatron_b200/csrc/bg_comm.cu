@@ -1345,29 +1345,53 @@ __global__ void __launch_bounds__(256, 2) all_reduce_nvls_kernel(char* mc, const
     const size_t per = (vecs + s.n - 1) / s.n;
     const size_t lo = per * s.me, hi = lo + per < vecs ? lo + per : vecs;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t v = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < hi; v += stride) {
-        uint4 out;
-        if (kBf16) {
-            uint4 in = mm_ld_reduce_bf16(mc + v * 16);
-            if (scale != 1.0f) {
-                float f[8];
-                unpack8(in, f);
+    constexpr int kU = 4;                // in-switch reductions in flight per thread
+    for (size_t v0 = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < hi; v0 += stride * kU) {
+        uint4 val[kU];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] *= scale;
-                in = pack8(f);
+        for (int u = 0; u < kU; ++u) {
+            const size_t v = v0 + (size_t)u * stride;
+            if (v < hi) {
+                if (kBf16) {
+                    val[u] = mm_ld_reduce_bf16(mc + v * 16);
+                } else {
+                    float4 in = mm_ld_reduce_f32(mc + v * 16);
+                    val[u] = make_uint4(__float_as_uint(in.x), __float_as_uint(in.y), __float_as_uint(in.z), __float_as_uint(in.w));
+                }
             }
-            out = in;
-        } else {
-            float4 in = mm_ld_reduce_f32(mc + v * 16);
-            out.x = __float_as_uint(in.x * scale); out.y = __float_as_uint(in.y * scale);
-            out.z = __float_as_uint(in.z * scale); out.w = __float_as_uint(in.w * scale);
         }
-        mm_st_16(mc + v * 16, out);
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const size_t v = v0 + (size_t)u * stride;
+            if (v < hi) {
+                uint4 out = val[u];
+                if (scale != 1.0f) {
+                    if (kBf16) {
+                        float f[8];
+                        unpack8(out, f);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] *= scale;
+                        out = pack8(f);
+                    } else {
+                        out.x = __float_as_uint(__uint_as_float(out.x) * scale); out.y = __float_as_uint(__uint_as_float(out.y) * scale);
+                        out.z = __float_as_uint(__uint_as_float(out.z) * scale); out.w = __float_as_uint(__uint_as_float(out.w) * scale);
+                    }
+                }
+                mm_st_16(mc + v * 16, out);
+            }
+        }
     }
     sync_peers<true, true, true>(s);     // my stores are visible everywhere and everyone's slice has landed here
     if (dst != nullptr) {
-        for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < vecs; v += stride)
-            st16(dst + v * 16, ld16_stream(local + v * 16));
+        for (size_t v0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < vecs; v0 += stride * kU) {
+            uint4 val[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (v0 + (size_t)u * stride < vecs) val[u] = ld16_stream(local + (v0 + (size_t)u * stride) * 16);
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (v0 + (size_t)u * stride < vecs) st16(dst + (v0 + (size_t)u * stride) * 16, val[u]);
+        }
         // the buffer may be refilled by the next call's producers only after every member has finished reading it: the next
         // call's entry barrier cannot give that (it waits for producers, not consumers), so leave through a barrier
         sync_peers<true, false, false>(s);

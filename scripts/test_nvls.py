@@ -90,12 +90,14 @@ def main():
             fill(); torch.cuda.synchronize(); dist.barrier()
             nvls_ms = timed(lambda: comm.all_reduce_nvls(grp, 0, out, elems, dtype))
             fill(); torch.cuda.synchronize(); dist.barrier()
+            inplace_ms = timed(lambda: comm.all_reduce_nvls(grp, 0, None, elems, dtype))   # result left in the buffer (no copy-out)
+            fill(); torch.cuda.synchronize(); dist.barrier()
             p2p_ms = timed(lambda: comm.all_reduce(grp, buf, out, elems=elems))
             nccl_ms = timed(lambda: dist.all_reduce(ref))
             bus = lambda ms: round(nbytes * 2 * (world - 1) / world / ms / 1e6, 1)  # noqa: E731
             if rank == 0:
                 print(json.dumps({"op": "all_reduce", "dtype": str(dtype), "bytes": nbytes, "p": world, "nvls_ms": round(nvls_ms, 4),
-                                  "nvls_busGBps": bus(nvls_ms), "ours_p2p_ms": round(p2p_ms, 4), "ours_p2p_busGBps": bus(p2p_ms),
+                                  "nvls_busGBps": bus(nvls_ms), "nvls_inplace_ms": round(inplace_ms, 4), "nvls_inplace_busGBps": bus(inplace_ms), "ours_p2p_ms": round(p2p_ms, 4), "ours_p2p_busGBps": bus(p2p_ms),
                                   "nccl_ms": round(nccl_ms, 4), "nccl_busGBps": bus(nccl_ms), "max_rel_err_vs_nccl": round(err, 6),
                                   "ok": good}), flush=True)
     assert comm.error_flag() == 0
