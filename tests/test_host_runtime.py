@@ -41,6 +41,8 @@ WORLD2 = {
     "dp2_zero2": dict(default_dp_type="zero2"),
     "dp2_zero3_ckpt_chunks2": dict(sdp=1, global_checkpoint=1, chunks=2),
     "dp2_ddp_chunks2": dict(default_dp_type="ddp", chunks=2),
+    # --reduce_in_fp32 (fp32 unsharded gradients and reduction, arguments.py:187) and --entropy_in_fp32 (:192)
+    "dp2_zero2_reduce_fp32_chunks2": dict(default_dp_type="zero2", chunks=2, reduce_in_fp32=True, entropy_in_fp32=True),
     "dp2_zero3_nopool": dict(sdp=1, embed_sdp=1, zero3_pool_slots=0),
     "dp2_zero3_pool2": dict(sdp=1, embed_sdp=1, zero3_pool_slots=2),
     "dp2_zero3_pool2_no_async_chunks2": dict(sdp=1, embed_sdp=1, zero3_pool_slots=2, chunks=2, async_grad_reduce=False),
