@@ -65,12 +65,20 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
     allreduce_dgrad:   all-reduce dgrad over the TP group (what ``copy_to_tensor_model_parallel_region`` does in
         backward, mappings_group.py:139) -- done here so the dgrad GEMM can write into the staging buffer.
     out_staged:        write y into the staging buffer (it is about to be all-reduced / reduce-scattered).
+    recompute:         (opt-in, ``--recompute_activations``) instead of saving ``input`` for the wgrad GEMM, save what it was made
+        from -- ("swiglu", gate_up) or ("rmsnorm", x, norm_weight, eps), tensors the producing op keeps anyway -- and redo that
+        elementwise pass in backward: one layer then holds 352 MiB less at Llama-3-8B / seq 8192.
     """
 
     @staticmethod
-    def forward(ctx, input, weight, sequence_parallel, allreduce_dgrad, out_staged, tp_group, reduce_scatter_out=False):
+    def forward(ctx, input, weight, sequence_parallel, allreduce_dgrad, out_staged, tp_group, reduce_scatter_out=False,
+                recompute_kind=None, recompute_eps=0.0, *recipe):
         be = get_backend()
-        ctx.save_for_backward(input, weight)
+        ctx.recompute = (recompute_kind, recompute_eps, len(recipe)) if recompute_kind else None
+        if ctx.recompute:
+            ctx.save_for_backward(weight, *recipe)
+        else:
+            ctx.save_for_backward(input, weight)
         ctx.reduce_scatter_out = reduce_scatter_out and _size(tp_group) > 1
         if ctx.reduce_scatter_out:
             # row-parallel forward under Megatron-SP (layers.py:1061-1109): GEMM + reduce-scatter along the sequence
@@ -100,7 +108,18 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_output):
         be = get_backend()
-        input, weight = ctx.saved_tensors
+        if ctx.recompute:
+            kind, eps, n_recipe = ctx.recompute
+            weight, recipe = ctx.saved_tensors[0], ctx.saved_tensors[1:]
+            if kind == "swiglu":
+                input = be.swiglu_fwd(recipe[0])
+            elif kind == "rmsnorm":
+                input, _ = be.rmsnorm_fwd(recipe[0], recipe[1], eps)
+            else:
+                raise ValueError("unknown recompute recipe %r" % (kind,))
+        else:
+            n_recipe = 0
+            input, weight = ctx.saved_tensors
         group = ctx.tp_group
         if ctx.reduce_scatter_out:   # backward of the reduce-scatter is an all-gather along the sequence (mappings_group.py:243-258)
             grad_output = be.all_gather_first_dim(grad_output.contiguous(), group)
@@ -128,15 +147,23 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
                     grad_input = be.all_reduce(staged.view(*full_shape), group)
             else:
                 grad_input = be.gemm(dy2d, weight, "nn").view(*grad_output.shape[:-1], k)
-        return grad_input, grad_weight, None, None, None, None, None
+        return (grad_input, grad_weight, None, None, None, None, None, None, None) + (None,) * n_recipe
 
 
 def linear_with_grad_accumulation_and_async_allreduce(input, weight, bias=None, gradient_accumulation_fusion=False,
                                                       async_grad_allreduce=False, sequence_parallel=False, tp_group=None,
-                                                      out_staged=False, reduce_scatter_out=False):
-    """Same call shape as layers.py:550-648 (``async_grad_allreduce`` here means "all-reduce dgrad over tp_group")."""
-    out = LinearWithGradAccumulationAndAsyncCommunication.apply(input, weight, sequence_parallel, async_grad_allreduce,
-                                                                out_staged, tp_group, reduce_scatter_out)
+                                                      out_staged=False, reduce_scatter_out=False, recompute=None):
+    """Same call shape as layers.py:550-648 (``async_grad_allreduce`` here means "all-reduce dgrad over tp_group").
+    ``recompute``: None, ("swiglu", gate_up) or ("rmsnorm", x, norm_weight, eps) -- see the Function's docstring."""
+    if recompute is None:
+        out = LinearWithGradAccumulationAndAsyncCommunication.apply(input, weight, sequence_parallel, async_grad_allreduce,
+                                                                    out_staged, tp_group, reduce_scatter_out)
+    else:
+        kind = recompute[0]
+        eps = float(recompute[3]) if kind == "rmsnorm" else 0.0
+        recipe = recompute[1:3] if kind == "rmsnorm" else recompute[1:2]
+        out = LinearWithGradAccumulationAndAsyncCommunication.apply(input, weight, sequence_parallel, async_grad_allreduce,
+                                                                    out_staged, tp_group, reduce_scatter_out, kind, eps, *recipe)
     return out if bias is None else out + bias
 
 
@@ -179,12 +206,12 @@ class ColumnParallelLinear(_ParallelLinearBase):
         else:
             self.register_parameter("bias", None)
 
-    def forward(self, input_):
+    def forward(self, input_, recompute=None):
         bias = self.bias if not self.skip_bias_add else None
         # without SP the input is replicated: dgrad must be all-reduced (copy_to_tensor_model_parallel_region, :875)
         out = linear_with_grad_accumulation_and_async_allreduce(
             input_, self.weight, bias, async_grad_allreduce=not self.sequence_parallel,
-            sequence_parallel=self.sequence_parallel, tp_group=self.tp_group)
+            sequence_parallel=self.sequence_parallel, tp_group=self.tp_group, recompute=recompute)
         if self.gather_output:
             assert not self.sequence_parallel
             out = gather_from_tensor_model_parallel_region_group(out, self.tp_group)
@@ -218,18 +245,19 @@ class RowParallelLinear(_ParallelLinearBase):
         else:
             self.register_parameter("bias", None)
 
-    def forward(self, input_):
+    def forward(self, input_, recompute=None):
         if not self.input_is_parallel:
             input_ = scatter_to_tensor_model_parallel_region_group(input_, self.tp_group)
+            recompute = None
         if self.sequence_parallel:
             # GEMM and the sequence reduce-scatter (:1109, C8) are one operation: partial tiles go straight to their owner
             out = linear_with_grad_accumulation_and_async_allreduce(
                 input_, self.weight, None, async_grad_allreduce=False, sequence_parallel=False, tp_group=self.tp_group,
-                reduce_scatter_out=True)
+                reduce_scatter_out=True, recompute=recompute)
         else:
             out_parallel = linear_with_grad_accumulation_and_async_allreduce(
                 input_, self.weight, None, async_grad_allreduce=False, sequence_parallel=False, tp_group=self.tp_group,
-                out_staged=True)
+                out_staged=True, recompute=recompute)
             out = reduce_from_tensor_model_parallel_region_group(out_parallel, self.tp_group)     # :1114 (C5)
         if not self.skip_bias_add and self.bias is not None:
             out = out + self.bias

@@ -173,6 +173,14 @@ def _cp_attention(q, k, v, group, scale):
     return torch.cat(outs, 1)
 
 
+def _recompute_activations():
+    try:
+        from ..arguments import get_args
+        return bool(getattr(get_args(), "recompute_activations", False))
+    except RuntimeError:
+        return False
+
+
 def _attention(q, k, v, causal, scale):
     be = get_backend()
     fn = getattr(be, "attention", None)
@@ -196,12 +204,15 @@ class ParallelMLP(nn.Module):
         self.dense_4h_to_h = RowParallelLinear(ffn, config.hidden_size, config=config, bias=False, input_is_parallel=True,
                                                tp_group=tp_group, params_dtype=params_dtype, device=device)
 
-    def forward(self, hidden_states):
-        inter, _ = self.dense_h_to_4h(hidden_states)
+    def forward(self, hidden_states, input_recipe=None):
+        gate_up, _ = self.dense_h_to_4h(hidden_states, recompute=input_recipe)
         if self.gated:
-            inter = _SwigluFn.apply(inter)
-        else:
-            inter = torch.nn.functional.gelu(inter)
+            inter = _SwigluFn.apply(gate_up)
+            # --recompute_activations: the 4h->h GEMM keeps gate_up (which SwiGLU's own backward holds anyway) instead of the
+            # SwiGLU output and redoes the elementwise pass in backward
+            recipe = ("swiglu", gate_up) if _recompute_activations() else None
+            return self.dense_4h_to_h(inter, recompute=recipe)
+        inter = torch.nn.functional.gelu(gate_up)
         return self.dense_4h_to_h(inter)
 
 
@@ -238,9 +249,10 @@ class ParallelAttention(nn.Module):
                                        input_is_parallel=True, tp_group=tp_group, params_dtype=params_dtype, device=device)
         self.softmax_scale = 1.0 / math.sqrt(self.hn)
 
-    def forward(self, hidden_states, attention_mask=None, encoder_output=None, inference_params=None, rotary_pos_emb=None):
+    def forward(self, hidden_states, attention_mask=None, encoder_output=None, inference_params=None, rotary_pos_emb=None,
+                input_recipe=None):
         # hidden_states [sq, b, h]; rotary_pos_emb = (cos, sin) fp32 tables [sq_local, hn/2] for this rank's positions
-        mixed, _ = self.query_key_value(hidden_states)                     # [s, b, ng*(r+2)*hn]
+        mixed, _ = self.query_key_value(hidden_states, recompute=input_recipe)   # [s, b, ng*(r+2)*hn]
         cos, sin = rotary_pos_emb
         stage_group = self.sp_group if self.use_ulysses else None
         q, k, v = _QkvRopeFn.apply(mixed, cos, sin, self.ng_local, self.r, self.hn, stage_group)

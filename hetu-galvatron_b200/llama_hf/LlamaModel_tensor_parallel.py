@@ -43,6 +43,7 @@ class LlamaAttention_tp(nn.Module):
         self.LayerNorm = RMSNorm(config.hidden_size, eps=config.rms_norm_eps, device="meta", sequence_parallel=megatron_sp)
         self.rotary_base = mconf.rotary_base
         self._rope_cache = {}
+        self.recompute_activations = bool(getattr(get_args(), "recompute_activations", False))
 
     def _rope(self, local_seq, offset, device):
         key = (local_seq, offset)
@@ -79,7 +80,8 @@ class LlamaAttention_tp(nn.Module):
             rope = self._rope_zigzag(seq, hidden_states.device)
         else:
             rope = self._rope(seq, offset, hidden_states.device)
-        out, _ = self.attention(hidden_states, attention_mask, rotary_pos_emb=rope)
+        recipe = ("rmsnorm", residual, self.LayerNorm.weight, self.LayerNorm.eps) if self.recompute_activations else None
+        out, _ = self.attention(hidden_states, attention_mask, rotary_pos_emb=rope, input_recipe=recipe)
         return out + residual
 
 
@@ -90,13 +92,15 @@ class LlamaMLP_tp(nn.Module):
         mconf = core_transformer_config_from_args(args)
         self.tp_group = tp_group.group if tp_group is not None else None
         self.mlp = ParallelMLP(mconf, tp_group=self.tp_group, device="meta")
+        self.recompute_activations = bool(getattr(args, "recompute_activations", False))
         megatron_sp = bool(args.sequence_parallel) and (tp_group is not None and tp_group.size > 1)
         self.LayerNorm = RMSNorm(config.hidden_size, eps=config.rms_norm_eps, device="meta", sequence_parallel=megatron_sp)
 
     def forward(self, hidden_states):
         residual = hidden_states
         hidden_states = self.LayerNorm(hidden_states)
-        out, _ = self.mlp(hidden_states)
+        recipe = ("rmsnorm", residual, self.LayerNorm.weight, self.LayerNorm.eps) if self.recompute_activations else None
+        out, _ = self.mlp(hidden_states, input_recipe=recipe)
         return out + residual
 
 

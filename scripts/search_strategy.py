@@ -35,13 +35,15 @@ def build_dp_core():
     return out_dir
 
 
-def llama3_8b_profiles(layer_ms, other_ms, seq):
+def llama3_8b_profiles(layer_ms, other_ms, seq, recompute_activations=False):
     h, ffn, nh, nkv, V = 4096, 14336, 32, 8, 128256
     hn = h // nh
     layer_params = (nh + 2 * nkv) * hn * h + nh * hn * h + 3 * ffn * h + 2 * h
     mb = lambda nbytes: nbytes / 2 ** 20  # noqa: E731
     # saved activations of one layer per sample (bf16): x, normed x, q/k/v, attn out, h1, normed h1, gate_up, act (+ fp32 lse / rstd)
     act_full = mb(seq * (h * 2 * 5 + (nh + 2 * nkv) * hn * 2 + 2 * ffn * 2 + ffn * 2) + seq * (nh + 2) * 4)
+    if recompute_activations:   # --recompute_activations: the SwiGLU output and the two RMSNorm outputs are not kept
+        act_full -= mb(seq * (ffn * 2 + 2 * h * 2))
     # tensor parallel shards everything except the two layer inputs + norm outputs (no sequence parallel): approx split
     act = {"1": act_full}
     for t in (2, 4, 8):
@@ -91,6 +93,8 @@ def main():
     ap.add_argument("--gpus", type=int, nargs="*", default=[1, 2, 4, 8])
     ap.add_argument("--hardware-dir", default=os.path.join(ROOT, "configs", "hardware_b200"),
                     help="measured tables from scripts/emit_hardware_profile.py (used when present; else the latency+bandwidth model)")
+    ap.add_argument("--recompute-activations", action="store_true",
+                    help="memory profile of the runtime's --recompute_activations mode (NOT the bench default; measure before use)")
     ap.add_argument("--debug-memory", action="store_true", help="print the engine's per-layer memory model for the dp-only strategy")
     opts = ap.parse_args()
 
@@ -104,7 +108,7 @@ def main():
     work = os.path.join(ROOT, "configs", "search_profiles")
     os.makedirs(work, exist_ok=True)
     model_name = "llama3-8b_seqlen%d" % opts.seq
-    time_cfg, mem_cfg = llama3_8b_profiles(opts.layer_ms, opts.other_ms, opts.seq)
+    time_cfg, mem_cfg = llama3_8b_profiles(opts.layer_ms, opts.other_ms, opts.seq, opts.recompute_activations)
     json.dump(time_cfg, open(os.path.join(work, "computation_profiling_bf16_%s.json" % model_name), "w"), indent=2)
     json.dump(mem_cfg, open(os.path.join(work, "memory_profiling_bf16_%s.json" % model_name), "w"), indent=2)
     results = {}

@@ -33,6 +33,8 @@ def launch(world, config, timeout=600, backend="oracle"):
 WORLD1 = {
     "plain": dict(),
     "ckpt_chunks2": dict(global_checkpoint=1, chunks=2),
+    # --recompute_activations: wgrad inputs (SwiGLU / RMSNorm outputs) are redone in backward instead of saved
+    "recompute_activations": dict(recompute_activations=True),
     "ddp_no_async": dict(default_dp_type="ddp", chunks=2, async_grad_reduce=False),
     "zero3": dict(sdp=1),
 }
@@ -56,6 +58,8 @@ WORLD2 = {
         "pp_deg": 1, "tp_sizes_enc": "1,1", "tp_consecutive_flags": "1,1", "dp_types_enc": "0,0", "use_sp": "0,0", "cp_sizes_enc": "2,2",
         "checkpoint": "0,0", "global_bsz": 4, "chunks": 1, "default_dp_type": "zero2", "vtp": 1, "vsp": 0, "vcp": 1}),
     "tp2_megatron_sp": dict(global_tp_deg=2, vocab_tp=2, sequence_parallel=True),
+    "tp2_megatron_sp_recompute_activations": dict(global_tp_deg=2, vocab_tp=2, sequence_parallel=True, recompute_activations=True),
+    "dp2_zero3_ckpt_recompute_activations": dict(sdp=1, embed_sdp=1, global_checkpoint=1, zero3_pool_slots=2, recompute_activations=True),
     # shapes the fused GEMM+reduce-scatter accepts (M = 256 = p x 128): on the GPU the row-parallel forward and the
     # column-parallel dgrad run as ONE kernel pair inside the model (forced: these K are below the profitability threshold)
     "tp2_megatron_sp_fused_gemm_rs": dict(global_tp_deg=2, vocab_tp=2, sequence_parallel=True, _spec={"n_positions": 256},
@@ -121,6 +125,9 @@ WORLD8 = {
 def test_world1(name):
     rep = launch(1, dict(WORLD1[name]))
     assert rep["max_grad_err"] < 3e-2
+    if name == "recompute_activations":     # same deterministic ops, redone: identical numbers
+        base = launch(1, dict(WORLD1["plain"]))
+        assert rep["losses"] == base["losses"] and rep["max_grad_err"] == base["max_grad_err"]
 
 
 @pytest.mark.parametrize("name", sorted(WORLD2))
@@ -142,6 +149,9 @@ def test_world2(name):
         assert rep["loss"] == base["loss"] and rep["loss_step1"] == base["loss_step1"]
     if name == "dp2_zero3_nopool":
         assert rep["pools"] == {}
+    if name == "tp2_megatron_sp_recompute_activations":
+        base = launch(2, dict(WORLD2["tp2_megatron_sp"]))
+        assert rep["losses"] == base["losses"] and rep["max_grad_err"] == base["max_grad_err"]
 
 
 @pytest.mark.parametrize("name", sorted(WORLD4))
