@@ -25,6 +25,18 @@ REF = "/root/reference"
 
 
 def build_dp_core():
+    """oracle/build_ref.py owns the recipe (also run by __graft_entry__.build())."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_oracle_build", os.path.join(ROOT, "oracle", "build_ref.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    so = mod.build()
+    if so is None:
+        raise SystemExit("the reference sources are not present: the Search Engine cannot run here")
+    return os.path.dirname(so)
+
+
+def build_dp_core_legacy():
     out_dir = os.path.join(ROOT, "oracle", "_ref")
     os.makedirs(out_dir, exist_ok=True)
     import sysconfig
