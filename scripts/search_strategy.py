@@ -36,17 +36,6 @@ def build_dp_core():
     return os.path.dirname(so)
 
 
-def build_dp_core_legacy():
-    out_dir = os.path.join(ROOT, "oracle", "_ref")
-    os.makedirs(out_dir, exist_ok=True)
-    import sysconfig
-    so = os.path.join(out_dir, "galvatron_dp_core" + sysconfig.get_config_var("EXT_SUFFIX"))
-    if not os.path.exists(so):
-        inc = subprocess.check_output([sys.executable, "-m", "pybind11", "--includes"], text=True).split()
-        subprocess.check_call(["g++", "-O3", "-shared", "-std=c++17", "-fPIC", *inc, os.path.join(REF, "csrc", "dp_core.cpp"), "-o", so])
-    return out_dir
-
-
 def llama3_8b_profiles(layer_ms, other_ms, seq, recompute_activations=False):
     h, ffn, nh, nkv, V = 4096, 14336, 32, 8, 128256
     hn = h // nh
