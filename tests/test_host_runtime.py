@@ -106,7 +106,21 @@ WORLD4 = {
 _HYBRID = dict(tp_consecutive_flags="1,1,1,1", use_sp="0,1,0,1", checkpoint="0,0,1,1", global_bsz=32,
                pipeline_type="pipedream_flush", default_dp_type="zero2")
 _SPEC8 = {"n_heads": 8, "n_kv_heads": 8, "n_layers": 4}
+def _redistributed(tp, vtp, sp):
+    """tests/core/test_redistributed.py:49-69,141-146: zero2, no checkpointing, per-layer tp lists that force a relocation between
+    every pair of layers and between the layers and the vocabulary rows, with and without Megatron sequence parallelism."""
+    return dict(_spec=_SPEC8, sequence_parallel=sp, _strategy_json=dict(
+        pp_deg=1, tp_sizes_enc=tp, tp_consecutive_flags="1,1,1,1", dp_types_enc="0,0,0,0", use_sp="0,0,0,0", checkpoint="0,0,0,0",
+        global_bsz=32, chunks=2, pp_division="4", pipeline_type="pipedream_flush", default_dp_type="zero2", vtp=vtp, vsp=0))
+
+
 WORLD8 = {
+    "ref_redistributed_tp1248_vtp8": _redistributed("1,2,4,8", 8, False),
+    "ref_redistributed_tp1248_vtp8_sp": _redistributed("1,2,4,8", 8, True),
+    "ref_redistributed_tp2821_vtp4": _redistributed("2,8,2,1", 4, False),
+    "ref_redistributed_tp2821_vtp4_sp": _redistributed("2,8,2,1", 4, True),
+    "ref_redistributed_tp8412_vtp2": _redistributed("8,4,1,2", 2, False),
+    "ref_redistributed_tp8412_vtp2_sp": _redistributed("8,4,1,2", 2, True),
     "ref_hybrid0_pp1_vtp2": dict(_spec=_SPEC8, sequence_parallel=True, _strategy_json=dict(_HYBRID, pp_deg=1, tp_sizes_enc="1,2,4,8", dp_types_enc="0,1,0,1",
                                                                   chunks=2, pp_division="4", vtp=2, vsp=0)),
     "ref_hybrid1_pp1_vsp4": dict(_spec=_SPEC8, sequence_parallel=True, _strategy_json=dict(_HYBRID, pp_deg=1, tp_sizes_enc="1,2,4,8", dp_types_enc="1,0,1,0",
