@@ -74,6 +74,12 @@ WORLD2 = {
 
 WORLD4 = {
     "tp2_dp2_sp_zero2": dict(global_tp_deg=2, vocab_tp=2, sequence_parallel=True, default_dp_type="zero2", chunks=2),
+    # tests/core/test_pp.py:126-128 (pp 4, both schedules, 8 microbatches) and test_tp.py:132-133 (tp 4: plain, Megatron-SP, Ulysses)
+    "pp4_1f1b_chunks8": dict(pp_deg=4, chunks=8, pipeline_type="pipedream_flush", global_train_batch_size=8, _spec={"n_layers": 4}),
+    "pp4_gpipe_chunks2": dict(pp_deg=4, chunks=2, pipeline_type="gpipe", _spec={"n_layers": 4}),
+    "tp4": dict(global_tp_deg=4, vocab_tp=4, chunks=2, _spec={"n_kv_heads": 4}),
+    "tp4_megatron_sp": dict(global_tp_deg=4, vocab_tp=4, sequence_parallel=True, chunks=2, _spec={"n_kv_heads": 4}),
+    "tp4_ulysses": dict(global_tp_deg=4, vocab_tp=4, use_ulysses=True, sequence_parallel=True, chunks=2, _spec={"n_kv_heads": 4}),
     "pp2_tp2_1f1b": dict(pp_deg=2, global_tp_deg=2, vocab_tp=2, chunks=2, pipeline_type="pipedream_flush"),
     # BASELINE config (3) shape: PP2 x TP2 x ZeRO-2 with Megatron-SP, 1F1B-flush, 4 microbatches
     "baseline3_pp2_tp2_sp_zero2": dict(pp_deg=2, global_tp_deg=2, vocab_tp=2, sequence_parallel=True, default_dp_type="zero2",
