@@ -100,7 +100,7 @@ def main():
     else:
         from oracle.gloo_backend import OracleBackend
         dist.init_process_group("gloo", rank=rank, world_size=world)
-        torch.set_num_threads(2)
+        torch.set_num_threads(1 if world >= 4 else 2)
         be = set_backend(OracleBackend())
         dev = torch.device("cpu")
     if strategy is not None:

@@ -19,7 +19,7 @@ def launch(world, config, timeout=600, backend="oracle"):
     extra_env = config.pop("_env", {})
     for rank in range(world):
         env = dict(os.environ, **extra_env, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
-                   MASTER_PORT=str(_PORT[0] + os.getpid() % 500), HOST_TEST_CONFIG=json.dumps(config), OMP_NUM_THREADS="2",
+                   MASTER_PORT=str(_PORT[0] + os.getpid() % 500), HOST_TEST_CONFIG=json.dumps(config), OMP_NUM_THREADS="1" if world >= 4 else "2",
                    HOST_TEST_BACKEND=backend)
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_host_worker.py")], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
