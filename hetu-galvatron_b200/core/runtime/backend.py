@@ -273,6 +273,19 @@ class CudaBackend:
                              src_byte_offset=off)
         return out
 
+    def all_reduce_inplace(self, x, group):
+        """Sum ``x`` over ``group`` IN PLACE when that is possible without a copy: NVLS is on (and HGB_NVLS_INPLACE=1), ``x`` is a
+        contiguous view of the group's multicast-bound staging buffer and large enough.  Returns whether it did."""
+        if not (getattr(self, "nvls", False) and os.environ.get("HGB_NVLS_INPLACE", "0") == "1" and self.comm.has_nvls(group)):
+            return False
+        buf = self._staging.get(tuple(group.ranks))
+        nbytes = x.numel() * x.element_size()
+        if (buf is None or not x.is_contiguous() or not self._is_staging(x, buf) or x.dtype not in (torch.bfloat16, torch.float32)
+                or nbytes < self.NVLS_MIN_BYTES or nbytes % 16):
+            return False
+        self.comm.all_reduce_nvls(group, x.data_ptr() - buf.u8.data_ptr(), None, x.numel(), x.dtype)
+        return True
+
     def _all_reduce_padded(self, x, group, op, out):
         n = x.numel()
         padded = (n + 7) // 8 * 8
