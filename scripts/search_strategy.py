@@ -96,6 +96,8 @@ def main():
                     help="measured tables from scripts/emit_hardware_profile.py (used when present; else the latency+bandwidth model)")
     ap.add_argument("--recompute-activations", action="store_true",
                     help="memory profile of the runtime's --recompute_activations mode (NOT the bench default; measure before use)")
+    ap.add_argument("--out-root", default=os.path.join(ROOT, "configs"),
+                    help="where search_profiles/ and searched/ are written (tests point this at a temp dir)")
     ap.add_argument("--debug-memory", action="store_true", help="print the engine's per-layer memory model for the dp-only strategy")
     opts = ap.parse_args()
 
@@ -106,7 +108,7 @@ def main():
     from galvatron.core.search_engine.search_engine import GalvatronSearchEngine
     from tests.utils.search_args import SearchArgs
 
-    work = os.path.join(ROOT, "configs", "search_profiles")
+    work = os.path.join(opts.out_root, "search_profiles")
     os.makedirs(work, exist_ok=True)
     model_name = "llama3-8b_seqlen%d" % opts.seq
     time_cfg, mem_cfg = llama3_8b_profiles(opts.layer_ms, opts.other_ms, opts.seq, opts.recompute_activations)
@@ -168,7 +170,7 @@ def main():
             continue
         cfg = json.load(open(files[0]))
         results[n] = (thr, cfg)
-        dst = os.path.join(ROOT, "configs", "searched", "galvatron_config_llama3-8b_%dgpus.json" % n)
+        dst = os.path.join(opts.out_root, "searched", "galvatron_config_llama3-8b_%dgpus.json" % n)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         json.dump(cfg, open(dst, "w"), indent=4)
         print("N=%d predicted throughput %.4f samples/s -> %s" % (n, thr, dst))
