@@ -13,6 +13,16 @@ llama3-8b_<N>gpus.json`` (per-GPU batch fixed => weak scaling).  Prints ONE JSON
   e2e        the same loop with the tokens/labels copied from pinned host memory every step and the loss read back
   roofline   the dominant kernel (the tcgen05 GEMM): algorithmic FLOPs / CUDA-event launch time vs the measured cuBLAS peak
   cpu_baseline  the oracle CPU restatement (oracle/gloo_backend.py) on a bounded sample, rank 0 at N=1 only
+  probe      two steps on a FIXED batch that is the same on every rank and at every N (loss at init, loss after one update:
+             both are N-invariant, so a broken forward or update shows when the driver's N = 1/2/4/8 lines are compared) and,
+             at N >= 2, a checksum-of-checksums of the gradient reduction at full size (sum of the reduced shards == sum of the
+             unsharded gradients / d, per layer)
+  path_legs  (N >= 2) the collectives north_star names, each as a short fixed-strategy run of the SAME model in a child process
+             per rank (a failing leg cannot take the headline down): TP=N Megatron-SP (fused all-gather+GEMM / GEMM+reduce-
+             scatter), TP=N (fused GEMM+all-reduce, NVLS), Ulysses SP=N (all-to-all), PP=2 x TP=N/2 1F1B (peer-copy p2p),
+             ZeRO-3 + checkpointing (and Llama-3-70B ZeRO-3 at N=8, BASELINE config 5): tokens/s, per-collective achieved bus
+             GB/s against 900 nominal / 770 measured, and a parity check of the same strategy on the tiny model against the
+             oracle (tests/_host_worker.py: loss 5e-3, per-parameter gradients 3e-2 rel-L2).
 """
 import argparse
 import json
@@ -46,6 +56,11 @@ def parse():
     p.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                    help="fused: AdamW inside the gradient reduce-scatter kernel; torch: torch.optim.AdamW(fused=True) on fp32 grads")
     p.add_argument("--checkpoint-layers", type=int, default=-1, help="override: checkpoint the first k layers")
+    p.add_argument("--legs", default="auto", help="auto (all path legs at N >= 2), none, or a comma-separated list of leg names")
+    p.add_argument("--leg", default=None, help="internal: run ONE path leg in this process (spawned per rank by the headline run)")
+    p.add_argument("--leg-port", type=int, default=0, help="internal: rendezvous port of the leg")
+    p.add_argument("--total-budget-s", type=float, default=760.0, help="wall-clock budget of the whole bench.py run (legs are skipped beyond it)")
+    p.add_argument("--no-probe", action="store_true")
     return p.parse_args()
 
 
@@ -172,6 +187,72 @@ def synthetic_batches(args, config, n_steps, dp_idx, dp_size, pin):
     return out
 
 
+NVLINK_NOMINAL_GBS, NVLINK_MEASURED_GBS = 900.0, 770.0    # per direction per GPU; measured = peer copy (B200_PROFILING.md)
+T_START = time.time()
+
+
+def fixed_probe_batch(config, per_rank):
+    """The probe's batch: ``per_rank`` sequences, the same on every rank and at every N (generator seed 4321)."""
+    import numpy as np
+    import torch
+    rng = np.random.RandomState(4321)
+    seq = config.max_position_embeddings
+    lengths = rng.randint(seq // 2, seq + 1, (per_rank,))
+    ids = rng.randint(0, config.vocab_size, (per_rank, seq + 1))
+    ids[np.arange(seq + 1)[None, :] >= lengths[:, None]] = 0
+    x = torch.from_numpy(ids).long()
+    return x[:, :-1].contiguous(), x[:, 1:].contiguous()
+
+
+def reduction_checksum(model, step_fn, world):
+    """Checksum of checksums of the gradient reduction at FULL size (N >= 2): one extra step with the optimizer epilogue
+    switched off, so that every unit's reduce-scatter / all-reduce leaves its fp32 result; then, per unit and summed over the
+    job,  sum(reduced shards) must equal sum(unsharded bf16 gradients) * prescale * postscale (= / d).  Linear in the data,
+    independent of the size, exact up to fp32 rounding of the sums."""
+    import torch
+    import torch.distributed as dist
+    units = list(model.model.units)
+    saved = [(u, u.fused_opt) for u in units]
+    for u in units:
+        u.fused_opt = None
+    try:
+        step_fn()
+        torch.cuda.synchronize()
+        rows = []
+        for u in units:
+            d = u.group.size
+            g_in = u.g_flat.double()
+            s_in, a_in = g_in.sum() / d, g_in.abs().sum() / d
+            red = u.master_grad.double()
+            s_out = red.sum() / (d if u.dp_type == "ddp" else 1)
+            rows.append(torch.stack([s_in, s_out, a_in]))
+        t = torch.stack(rows)
+        dist.all_reduce(t)
+        rel = ((t[:, 0] - t[:, 1]).abs() / t[:, 2].clamp_min(1e-30))
+        worst = int(rel.argmax())
+        return {"units": len(units), "max_rel_discrepancy": float(rel.max()), "worst_unit": units[worst].name,
+                "ok": bool(rel.max() < 2e-4), "what": "sum_ranks(sum(reduced fp32 shard)) vs sum_ranks(sum(bf16 unsharded grads))/d, relative to sum|g|/d"}
+    finally:
+        for u, f in saved:
+            u.fused_opt = f
+            u._master_grad = None
+            u.flat_param.grad = None
+        torch.cuda.empty_cache()
+
+
+def summarize_comm(prof, steps):
+    """{kind: calls/step, ms/step, achieved bus GB/s (nccl-tests convention), fraction of 900 nominal / 770 measured}"""
+    out = {}
+    for kind, recs in sorted(prof.items()):
+        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in recs)
+        nbytes = sum(b for _, _, b in recs)
+        gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        out[kind] = {"calls_per_step": round(len(recs) / steps, 1), "ms_per_step": round(ms / steps, 3), "bus_bytes_per_step": int(nbytes / steps),
+                     "bus_GBps": round(gbs, 1), "frac_of_900_nominal": round(gbs / NVLINK_NOMINAL_GBS, 3),
+                     "frac_of_770_measured": round(gbs / NVLINK_MEASURED_GBS, 3)}
+    return out
+
+
 def run_ours(opts):
     os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")   # 150+ GiB of long-lived state: avoid fragmentation
     import torch
@@ -184,7 +265,7 @@ def run_ours(opts):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)   # bootstrap only (handles, barriers)
-    from hetu_galvatron_b200.core.runtime.backend import get_backend
+    from hetu_galvatron_b200.core.runtime.backend import get_backend, reset_backend
     from hetu_galvatron_b200.core.runtime.utils import get_optimizer_and_param_scheduler
     spath, strategy = strategy_for(world, opts.strategy)
     args, config, model = build_model(opts, strategy)
@@ -193,7 +274,7 @@ def run_ours(opts):
     dp_group = model.vtp_data_group
     dp_idx, dp_size = dp_group.rank_in_group(rank), dp_group.size
     K, W = opts.steps, opts.warmup
-    host = synthetic_batches(args, config, 2 * K + W, dp_idx, dp_size, pin=True)
+    host = synthetic_batches(args, config, 2 * K + W + 1, dp_idx, dp_size, pin=True)
     tokens_per_step = args.global_train_batch_size * config.max_position_embeddings
 
     def sync_all():
@@ -209,6 +290,23 @@ def run_ours(opts):
         return loss
 
     it = 0
+    # ---- probe: N-invariant losses on a fixed batch, then (N >= 2) the full-size checksum of the gradient reduction -------
+    probe = None
+    if not opts.no_probe:
+        pt, pl = fixed_probe_batch(config, args.global_train_batch_size // dp_size)
+        pt, pl = pt.to(dev), pl.to(dev)
+        l0 = step(pt, pl, it); it += 1
+        l1 = step(pt, pl, it); it += 1
+        probe = {"fixed_batch": "%d sequences, seed 4321, identical on every rank and at every N" % pt.shape[0],
+                 "loss_at_init": l0, "loss_after_one_update": l1, "finite": bool(l0 == l0 and l1 == l1)}
+        if world > 1:
+            both = torch.tensor([l0 if l0 is not None else 0.0, l1 if l1 is not None else 0.0], dtype=torch.float64, device=dev)
+            lo, hi = both.clone(), both.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            probe["max_spread_over_ranks"] = float((hi - lo).abs().max())
+            t, l = host[-1]
+            probe["reduction_checksum"] = reduction_checksum(
+                model, lambda: model.forward_backward([t.to(dev)], it, None, loss_func=None, attention_mask=None, labels=l.to(dev)), world)
     for i in range(W):                                         # warm-up (untimed)
         t, l = host[i]
         step(t.to(dev, non_blocking=True), l.to(dev, non_blocking=True), it); it += 1
@@ -244,7 +342,12 @@ def run_ours(opts):
     prof, be.gemm_profile = be.gemm_profile, None
     ms_e2e, _, loss_e2e = timed(resident=False)
     clocks = sampler.stop() if rank == 0 else None
+    # one more step with every collective bracketed by CUDA events on its own stream: the in-step NVLink roofline
+    be.comm_profile = {}
+    t, l = host[W]
+    step(t.to(dev), l.to(dev), it); it += 1
     torch.cuda.synchronize()
+    comm, be.comm_profile = summarize_comm(be.comm_profile, 1), None
     gemm_ms = sum(rec[0].elapsed_time(rec[1]) for rec in prof)
     gemm_flops = sum(rec[2] for rec in prof)
     gemm_bytes = sum(rec[3] for rec in prof)
@@ -263,7 +366,9 @@ def run_ours(opts):
                    "tp": sorted(set(strategy["tp_sizes_enc"].split(","))), "checkpointed_layers": strategy.get("checkpoint", "").count("1"),
                    "layers": config.num_hidden_layers, "l2": "inputs (16 GB of bf16 weights + activations per step) far exceed the 126 MB L2",
                    "optimizer": ("AdamW fused into the gradient reduce-scatter kernel (fp32 shards)" if opts.optimizer == "fused"
-                                 else "torch.optim.AdamW(fused=True) on fp32 flat shards")},
+                                 else "torch.optim.AdamW(fused=True) on fp32 flat shards"),
+                   "collectives": "slim peer-memory kernels (128 thr x <=64 regs, one CTA per SM)%s; no NCCL on the path"
+                                  % (", NVLS multicast for buffers in a bound arena range" if getattr(be, "nvls", False) else "")},
         "e2e": {"value": round(tokens_per_step * K / (ms_e2e * 1e-3), 1), "unit": "tokens/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4 * max(1, strategy["chunks"]), "ms_per_step": round(ms_e2e / K, 3)},
         "gpu_launches": int(launches),
@@ -272,22 +377,237 @@ def run_ours(opts):
                      "algorithmic_bytes_per_launch_avg": gemm_bytes / max(1, len(prof)), "kernel": "gemm_bf16_kernel (tcgen05/TMEM/TMA)",
                      "launches": len(prof), "kernel_ms_per_step": round(gemm_ms / K, 3), "share_of_step": round(gemm_ms / ms_res, 4),
                      "flops_per_launch_avg": gemm_flops / max(1, len(prof)), "peak_source": peak_src},
-        "clocks": clocks, "loss": {"resident": loss_res, "e2e": loss_e2e},
+        "collectives_in_step": comm,
+        "clocks": clocks, "loss": {"resident": loss_res, "e2e": loss_e2e}, "probe": probe,
         "memory_gib": {"torch_peak_allocated": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
                        "torch_peak_reserved": round(torch.cuda.max_memory_reserved() / 2 ** 30, 2),
                        "arena": round(be.comm.arena_bytes / 2 ** 30, 2)},
     }
     if opts.layers:
         line["invalid"] = "debug run with --layers %d: not the BASELINE workload" % opts.layers
+    # ---- release the GPU, then the path legs (N >= 2) or the CPU baseline (N = 1) ------------------------------------------
+    del model, opt, host, prof
+    reset_backend()
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    if world > 1 and opts.legs != "none":
+        try:
+            line["path_legs"] = run_path_legs(opts, rank, world, local)
+        except Exception as exc:  # noqa: BLE001 -- the headline line must be printed whatever happens to a leg
+            line["path_legs"] = [{"error": "%s: %s" % (type(exc).__name__, exc)}]
     if rank == 0 and world == 1 and not opts.no_cpu_baseline:
-        from hetu_galvatron_b200.core.runtime.backend import reset_backend
-        reset_backend()
         line["cpu_baseline"] = cpu_reference_sample(opts)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# path legs: fixed-strategy runs of the collectives north_star names, one child process per rank and leg
+# ---------------------------------------------------------------------------------------------------------------------
+def leg_catalog(n):
+    """name -> {model, strategy (Galvatron JSON, as the Search Engine would write it), tiny (the same strategy for the tiny model of
+    tests/_host_worker.py), expect (fused-kernel counters that must be > 0)}"""
+    def enc(v, layers=32):
+        return ",".join([str(v)] * layers)
+
+    def strat(layers=32, **kw):
+        d = {"pp_deg": 1, "tp_sizes_enc": enc(1, layers), "tp_consecutive_flags": enc(1, layers), "dp_types_enc": enc(0, layers),
+             "use_sp": enc(0, layers), "checkpoint": enc(0, layers), "cp_sizes_enc": enc(1, layers), "global_bsz": 8, "chunks": 2,
+             "pp_division": str(layers), "pipeline_type": "pipedream_flush", "default_dp_type": "zero2", "vtp": 1, "vsp": 0, "embed_sdp": 0}
+        d.update(kw)
+        return d
+    # tiny model whose GEMMs meet the fused kernels' shape rule (M = seq x microbatch a multiple of p x 128) at this p
+    heads = max(4, n)
+    spec = {"n_positions": 128 * n, "n_heads": heads, "n_kv_heads": max(2, n), "ffn_dim": 384, "dim": 128 if n < 8 else 256}
+    legs = {}
+    legs["tp%d_megatron_sp" % n] = dict(
+        model="llama3-8b", strategy=strat(tp_sizes_enc=enc(n), vtp=n, sequence_parallel=1),
+        tiny=dict(global_tp_deg=n, vocab_tp=n, sequence_parallel=True, chunks=2, _spec=spec,
+                  _env={"HGB_FUSE_GEMM_RS": "force", "HGB_FUSE_GEMM_AR": "force"}),
+        expect=["ag_gemm", "gemm_rs"], what="C7/C8/C9: all-gather+GEMM and GEMM+reduce-scatter fused (layers.py:399-417,1061-1109,449-494)")
+    legs["tp%d" % n] = dict(
+        model="llama3-8b", strategy=strat(tp_sizes_enc=enc(n), vtp=n, sequence_parallel=0),
+        tiny=dict(global_tp_deg=n, vocab_tp=n, chunks=2, _spec=spec, _env={"HGB_FUSE_GEMM_AR": "force"}),
+        expect=["gemm_ar"], what="C5/C6: GEMM+all-reduce fused, NVLS broadcast (layers.py:1110-1114, mappings_group.py:139)")
+    legs["ulysses%d" % n] = dict(
+        model="llama3-8b", strategy=strat(tp_sizes_enc=enc(n), use_sp=enc(1), vtp=n, vsp=1, sequence_parallel=1),
+        tiny=dict(global_tp_deg=n, vocab_tp=n, use_ulysses=True, sequence_parallel=True, chunks=2, _spec=spec),
+        expect=[], what="C10: Ulysses all-to-all, q/k/v in one launch (transformer.py:1928-2062)")
+    t2 = max(1, n // 2)
+    legs["pp2_tp%d_1f1b" % t2] = dict(
+        model="llama3-8b", strategy=strat(pp_deg=2, tp_sizes_enc=enc(t2), vtp=t2, sequence_parallel=1 if t2 > 1 else 0, chunks=4,
+                                          pp_division="16,16"),
+        tiny=dict(pp_deg=2, global_tp_deg=t2, vocab_tp=t2, sequence_parallel=t2 > 1, chunks=4, pipeline_type="pipedream_flush",
+                  global_train_batch_size=8, _spec=dict(spec, n_positions=128 * t2)),
+        expect=[], what="C11: 1F1B-flush schedule, stage boundary = peer copy on a side stream + device flags (pipeline.py:375-701,1080-1257)")
+    legs["zero3_ckpt_dp%d" % n] = dict(
+        model="llama3-8b", strategy=strat(dp_types_enc=enc(1), checkpoint=enc(1), global_bsz=2 * n, chunks=1, default_dp_type="zero3", embed_sdp=1),
+        tiny=dict(sdp=1, global_checkpoint=1, embed_sdp=1, chunks=1, global_train_batch_size=2 * n, zero3_pool_slots=2),
+        expect=[], what="C1/C2: ZeRO-3 all-gather (fwd + bwd re-gather) and reduce-scatter+AdamW per layer, pooled buffers, prefetch")
+    if n == 8:
+        legs["llama3-70b_zero3_ckpt_dp8"] = dict(
+            model="llama3-70b", strategy=strat(layers=80, dp_types_enc=enc(1, 80), checkpoint=enc(1, 80), global_bsz=8, chunks=1,
+                                               default_dp_type="zero3", embed_sdp=1),
+            tiny=None, expect=[], what="BASELINE config 5: Llama-3-70B SDP=8 ZeRO-3 + activation checkpointing (>= 0.40 s/step of NVLink time)")
+    return legs
+
+
+def _child_env(rank, world, local, port):
+    env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC") and k not in ("GROUP_RANK", "ROLE_RANK", "ROLE_NAME",
+                                                                                                  "GROUP_WORLD_SIZE", "ROLE_WORLD_SIZE")}
+    env.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(local), LOCAL_WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+               MASTER_PORT=str(port))
+    return env
+
+
+def run_path_legs(opts, rank, world, local):
+    """Every rank spawns ITS process of each leg (the leg's ranks rendezvous on their own port); rank 0 keeps the leg's JSON line.
+    The parent ranks stay in step through the bootstrap group; a leg that fails, hangs past its limit or would overrun the
+    wall-clock budget is recorded and skipped -- by the same decision on every rank."""
+    import torch
+    import torch.distributed as dist
+    catalog = leg_catalog(world)
+    names = list(catalog) if opts.legs == "auto" else [n for n in opts.legs.split(",") if n in catalog]
+    base_port = int(os.environ.get("MASTER_PORT", "29500")) + 11
+    results = []
+    for i, name in enumerate(names):
+        limit = 300.0 if "70b" in name else 170.0
+        decision = [None]
+        if rank == 0:
+            left = opts.total_budget_s - (time.time() - T_START)
+            decision[0] = "run" if left > limit * 0.6 + 20 else "skipped: %.0f s of the %.0f s budget left" % (left, opts.total_budget_s)
+        dist.broadcast_object_list(decision, src=0)
+        if decision[0] != "run":
+            results.append({"leg": name, "status": decision[0]})
+            continue
+        cmd = [sys.executable, os.path.abspath(__file__), "--leg", name, "--gpus", str(world), "--steps", "3", "--warmup", "2",
+               "--leg-port", str(base_port + 3 * i)]
+        t0 = time.time()
+        proc = subprocess.Popen(cmd, env=_child_env(rank, world, local, base_port + 3 * i), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        try:
+            out, err = proc.communicate(timeout=limit)
+            status = "ok" if proc.returncode == 0 else "failed rc=%d" % proc.returncode
+        except subprocess.TimeoutExpired:
+            proc.kill()                      # exactly the child this rank started
+            out, err = proc.communicate()
+            status = "killed after %.0f s" % limit
+        rec = {"leg": name, "status": status, "what": catalog[name]["what"], "wall_s": round(time.time() - t0, 1)}
+        if rank == 0:
+            for ln in out.splitlines():
+                if ln.startswith("LEG_JSON "):
+                    try:
+                        rec.update(json.loads(ln[len("LEG_JSON "):]))     # the last complete line wins (perf first, then + parity)
+                    except ValueError:
+                        pass
+            if status != "ok":
+                rec["stderr_tail"] = err[-600:]
+        # every rank's verdict: a leg counts as ok only if all its ranks exited cleanly
+        flag = torch.tensor([1 if status == "ok" else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag[0]) == 0 and status == "ok":
+            rec["status"] = "failed on another rank"
+        results.append(rec)
+    return results
+
+
+def run_leg(opts):
+    """One path leg, one process per GPU (spawned by ``run_path_legs``).  Prints ``LEG_JSON {...}`` on rank 0: first the
+    performance part, then again with the tiny-model parity verdict added."""
+    os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    leg = leg_catalog(world)[opts.leg]
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from hetu_galvatron_b200.core.runtime.backend import get_backend, reset_backend
+    from hetu_galvatron_b200.core.runtime.utils import get_optimizer_and_param_scheduler
+    strategy = dict(leg["strategy"])
+    lopts = argparse.Namespace(**vars(opts))
+    lopts.model, lopts.layers, lopts.checkpoint_layers, lopts.optimizer = leg["model"], 0, -1, "fused"
+    t_build = time.time()
+    args, config, model = build_model(lopts, strategy)
+    be = get_backend()
+    be.bg.set_tunable("timeout_ms", 45000)
+    opt, _ = get_optimizer_and_param_scheduler(model, args)
+    torch.cuda.synchronize()
+    build_s = time.time() - t_build
+    dp_group = model.vtp_data_group
+    dp_idx, dp_size = dp_group.rank_in_group(rank), dp_group.size
+    K, W = opts.steps, opts.warmup
+    host = synthetic_batches(args, config, K + W + 1, dp_idx, dp_size, pin=False)
+    tokens_per_step = args.global_train_batch_size * config.max_position_embeddings
+    it, losses = 0, []
+
+    def step(i):
+        nonlocal it
+        t, l = host[i]
+        loss = model.forward_backward([t.to(dev)], it, None, loss_func=None, attention_mask=None, labels=l.to(dev))
+        opt.step(); opt.zero_grad()
+        it += 1
+        return loss
+
+    for i in range(W):
+        losses.append(step(i))
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    launches0 = be.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(W, W + K):
+        losses.append(step(i))
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    tms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms[0])
+    launches = be.launch_count() - launches0
+    be.comm_profile = {}
+    step(W + K)
+    torch.cuda.synchronize()
+    comm, be.comm_profile = summarize_comm(be.comm_profile, 1), None
+    lt = torch.tensor([[x if x is not None else 0.0, 1.0 if x is not None else 0.0] for x in losses], dtype=torch.float64, device=dev)
+    dist.all_reduce(lt)                     # the last pipeline stage holds the loss; average the data-parallel replicas
+    mean_losses = [round(float(a / max(b, 1.0)), 5) for a, b in lt.tolist()]
+    rec = {"model": leg["model"], "seq": config.max_position_embeddings, "global_bsz": args.global_train_batch_size,
+           "strategy": {k: (strategy[k] if not isinstance(strategy[k], str) or len(strategy[k]) < 12 else strategy[k].split(",")[0] + " x%d" % len(strategy[k].split(",")))
+                        for k in ("pp_deg", "tp_sizes_enc", "use_sp", "dp_types_enc", "checkpoint", "chunks", "default_dp_type", "vtp", "vsp", "sequence_parallel") if k in strategy},
+           "tokens_per_s": round(tokens_per_step * K / (ms * 1e-3), 1), "ms_per_step": round(ms / K, 3), "steps": K, "warmup": W,
+           "gpu_launches": int(launches), "fused_calls": dict(getattr(be, "n_fused", {})), "nvls_groups": len(getattr(be, "nvls_regions", {}) or {}),
+           "collectives": comm, "losses": mean_losses, "build_s": round(build_s, 1),
+           "memory_gib": {"torch_peak_allocated": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2), "arena": round(be.comm.arena_bytes / 2 ** 30, 2)},
+           "expect_ok": all(getattr(be, "n_fused", {}).get(k, 0) > 0 for k in leg["expect"]), "device_error_flag": be.comm.error_flag()}
+    if rank == 0:
+        print("LEG_JSON " + json.dumps(rec), flush=True)
+    del model, opt, host
+    reset_backend()
+    dist.barrier()
+    dist.destroy_process_group()
+    import gc
+    gc.collect(); torch.cuda.empty_cache()
+    # ---- the same strategy on the tiny model against the oracle (checker: tests/_host_worker.py) -----------------------------
+    if leg["tiny"] is not None:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        tiny = dict(leg["tiny"])
+        for k, v in tiny.pop("_env", {}).items():
+            os.environ[k] = v
+        os.environ.update(HOST_TEST_CONFIG=json.dumps(tiny), HOST_TEST_BACKEND="cuda", MASTER_PORT=str(opts.leg_port + 1))
+        import _host_worker
+        try:
+            rep = _host_worker.main()
+            rec["parity"] = {"ok": True, "loss": rep.get("loss"), "oracle_loss": rep.get("ref_loss"), "max_grad_rel_l2": rep.get("max_grad_err"),
+                             "worst": rep.get("worst"), "fused_calls": rep.get("fused_calls"), "nvls_groups": rep.get("nvls_groups"),
+                             "criterion": "loss 5e-3 rel, every parameter's gradient 3e-2 rel-L2 vs oracle/llama_ref.py (bf16)"}
+        except BaseException as exc:  # noqa: BLE001
+            rec["parity"] = {"ok": False, "error": ("%s: %s" % (type(exc).__name__, exc))[:400]}
+        if rank == 0:
+            print("LEG_JSON " + json.dumps(rec), flush=True)
+        if not rec["parity"]["ok"]:
+            sys.exit(3)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -363,6 +683,8 @@ if __name__ == "__main__":
     o = parse()
     if o.impl == "reference":
         run_reference(o)
+    elif o.leg:
+        run_leg(o)
     else:
         try:
             run_ours(o)

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libbg_galvatron.so")
 BF16, F32 = 0, 1
 SUM, MAX = 0, 1
 MAX_PEERS = 8
-LANE_UNSHARD, LANE_REDUCE, LANE_ACT, LANE_MISC = 0, 1, 2, 3
+LANE_UNSHARD, LANE_REDUCE, LANE_ACT, LANE_MISC, LANE_PUSH = 0, 1, 2, 3, 4
 
 _c = ctypes
 _vp, _sz, _i, _ll, _f = _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_longlong, _c.c_float
@@ -56,6 +56,7 @@ SIGNATURES = {
     "bg_group_mc_create": (_i, [_vp, _i, _sz, _c.POINTER(_i)]),
     "bg_group_mc_join": (_i, [_vp, _i, _i, _sz]),
     "bg_group_mc_bind": (_i, [_vp, _i, _sz]),
+    "bg_group_mc_disable": (_i, [_vp, _i]),
     "bg_all_reduce_nvls": (_i, [_vp, _i, _i, _sz, _vp, _sz, _i, _c.c_float, _vp]),
     "bg_group_create": (_i, [_vp, _c.POINTER(_i), _i, _c.POINTER(_i)]),
     "bg_group_info": (_i, [_vp, _i, _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i)]),
@@ -81,10 +82,13 @@ SIGNATURES = {
     "bg_ce_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _ll, _ll, _ll, _vp]),
     "bg_gemm_bf16": (_i, [_vp, _vp, _vp, _ll, _ll, _ll, _i, _i, _vp]),
     "bg_gemm_reduce_scatter": (_i, [_vp, _i, _i, _vp, _vp, _ll, _ll, _ll, _i, _c.POINTER(_sz), _c.POINTER(_sz), _vp, _vp]),
+    "bg_gemm_all_reduce": (_i, [_vp, _i, _i, _vp, _vp, _ll, _ll, _ll, _i, _c.POINTER(_sz), _c.POINTER(_sz), _c.POINTER(_sz), _vp]),
+    "bg_all_gather_gemm": (_i, [_vp, _i, _i, _vp, _c.POINTER(_sz), _c.POINTER(_sz), _vp, _vp, _ll, _ll, _ll, _i, _vp, _vp]),
 }
 
 _lib = None
 _lib_lock = threading.Lock()
+_SERIAL = os.environ.get("HGB_SERIAL_COLLECTIVES", "0") == "1"
 
 
 class BgError(RuntimeError):
@@ -252,6 +256,13 @@ class BgComm:
         check(lib().bg_arena_info(self._ctx, ctypes.byref(base), ctypes.byref(nbytes), ctypes.byref(used)))
         self.arena_ptr, self.arena_bytes = base.value, nbytes.value
         self._arena_u8 = torch.as_tensor(_ArenaExport(self.arena_ptr, self.arena_bytes, self), device="cuda:%d" % self.device)
+        self._first_aligned = 0
+        if vmm:   # multicast ranges start on a multicast-granularity boundary behind the signal pad
+            gran = self.arena_mode()[2]
+            if gran:
+                o = _sz()
+                check(lib().bg_arena_alloc_aligned(self._ctx, 0, int(gran), ctypes.byref(o)))
+                self._first_aligned = o.value
         self._sym = {}       # key -> SymBuffer
         self._sym_seq = {}   # group ranks -> next sequence number
         self._pending = []   # SymBuffers whose peer offsets are not known yet
@@ -303,48 +314,90 @@ class BgComm:
             os.close(pfd)
         os.close(fd.value)
 
-    def setup_nvls(self, buffers, pg=None):
-        """Collective over the whole job (every rank calls it once, with ITS buffers): one multicast object per (group,
-        symmetric buffer).  The group's first rank creates the object and hands its descriptor to the members; everybody adds
-        its device; barrier; everybody binds its own arena range; barrier."""
+    def setup_nvls(self, pg=None):
+        """Collective over the whole job, after ``exchange()``: for every group of >= 2 ranks, ONE multicast object over the arena
+        range that holds the group's symmetric buffers (those that sit at the same offset on every member -- SPMD allocation
+        makes that the rule).  The group's first rank creates the object and hands its descriptor to the members; everybody
+        adds its device; barrier; everybody binds its own arena range; the outcome is agreed on by all ranks, and a group whose
+        setup failed anywhere simply keeps the peer-to-peer kernels.  Collectives on buffers inside a bound range then use the
+        switch on their own (multimem.st / multimem.ld_reduce), see include/bg_galvatron.h."""
         import torch.distributed as dist
         vmm, mc, gran = self.arena_mode()
         if not (vmm and mc):
-            raise BgError("NVLS needs a VMM arena on a multicast-capable device (arena_mode = %r)" % ((vmm, mc, gran),))
-        outgoing, expected, created = [], 0, {}
-        for buf in buffers:
+            return {}
+        regions = {}
+        for buf in self._sym.values():
+            if buf.group.size < 2 or buf.offsets is None or len(set(int(o) for o in buf.offsets)) != 1:
+                continue
             ranks = tuple(buf.group.ranks)
-            gid = self.group_id(buf.group)
-            if buf.offset % gran or buf.nbytes % gran:
-                raise BgError("NVLS buffer of group %s must be aligned to the multicast granularity %d" % (ranks, gran))
+            lo, hi = regions.get(ranks, (1 << 62, 0))
+            regions[ranks] = (min(lo, buf.offset), max(hi, buf.offset + buf.nbytes))
+        plan = []
+        for ranks in sorted(regions):
+            lo, hi = regions[ranks]
+            lo = max(lo // gran * gran, self._first_aligned)
+            hi = min((hi + gran - 1) // gran * gran, self.arena_bytes)
+            plan.append((ranks, lo, hi - lo))
+        ok = {ranks: True for ranks, _, _ in plan}
+        outgoing, expected, created = [], 0, {}
+        for ranks, lo, nbytes in plan:
+            gid = self._gid_of_ranks(ranks)
             if self.rank == ranks[0]:
-                fd = _i()
-                check(lib().bg_group_mc_create(self._ctx, gid, int(buf.nbytes), ctypes.byref(fd)))
+                fd = _i(-1)
+                if lib().bg_group_mc_create(self._ctx, gid, int(nbytes), ctypes.byref(fd)) != 0:
+                    ok[ranks] = False
+                    fd = _i(os.open(os.devnull, os.O_RDONLY))      # the members still expect a descriptor
                 created[ranks] = fd.value
-                outgoing += [(r, ("mc", ranks), fd.value) for r in ranks[1:]]
+                outgoing += [(r, ("mc", ranks, ok[ranks]), fd.value) for r in ranks[1:]]
             else:
                 expected += 1
         got = self._fd_channel.exchange(outgoing, expected) if self.world > 1 else {}
-        for buf in buffers:
-            ranks = tuple(buf.group.ranks)
-            gid = self.group_id(buf.group)
+        by_group = {tag[1]: (tag[2], fd) for (_src, tag), fd in got.items()}
+        for ranks, lo, nbytes in plan:
+            gid = self._gid_of_ranks(ranks)
             if self.rank == ranks[0]:
-                check(lib().bg_group_mc_join(self._ctx, gid, -1, int(buf.nbytes)))
+                if ok[ranks] and lib().bg_group_mc_join(self._ctx, gid, -1, int(nbytes)) != 0:
+                    ok[ranks] = False
                 os.close(created[ranks])
             else:
-                fd = got[(ranks[0], ("mc", ranks))]
-                check(lib().bg_group_mc_join(self._ctx, gid, fd, int(buf.nbytes)))
+                good, fd = by_group[ranks]
+                if not good or lib().bg_group_mc_join(self._ctx, gid, fd, int(nbytes)) != 0:
+                    ok[ranks] = False
                 os.close(fd)
         if self.world > 1:
             dist.barrier(group=pg)          # every device is in every object before anyone binds
-        for buf in buffers:
-            check(lib().bg_group_mc_bind(self._ctx, self.group_id(buf.group), int(buf.offset)))
-            self._nvls[tuple(buf.group.ranks)] = buf
+        for ranks, lo, nbytes in plan:
+            if ok[ranks] and lib().bg_group_mc_bind(self._ctx, self._gid_of_ranks(ranks), int(lo)) != 0:
+                ok[ranks] = False
         if self.world > 1:
-            dist.barrier(group=pg)
+            every = [None] * self.world
+            dist.all_gather_object(every, ok, group=pg)
+        else:
+            every = [ok]
+        for ranks, lo, nbytes in plan:
+            good = all(d.get(ranks, True) for d in every)
+            if good:
+                self._nvls[ranks] = (lo, nbytes)
+            else:
+                lib().bg_group_mc_disable(self._ctx, self._gid_of_ranks(ranks))
+        return dict(self._nvls)
 
-    def has_nvls(self, group):
-        return tuple(group.ranks) in self._nvls
+    def _gid_of_ranks(self, ranks):
+        gid = self._gids.get(tuple(ranks))
+        if gid is None:
+            arr = (_i * len(ranks))(*ranks)
+            out = _i()
+            check(lib().bg_group_create(self._ctx, arr, len(ranks), ctypes.byref(out)))
+            gid = self._gids[tuple(ranks)] = out.value
+        return gid
+
+    def has_nvls(self, group, buf=None, byte_offset=0, nbytes=0):
+        """Is ``group`` (and, if given, this range of its symmetric buffer) inside a multicast-bound arena range?"""
+        reg = self._nvls.get(tuple(group.ranks))
+        if reg is None or buf is None:
+            return reg is not None
+        return (buf.offsets is not None and len(set(int(o) for o in buf.offsets)) == 1 and buf.offset + byte_offset >= reg[0]
+                and buf.offset + byte_offset + nbytes <= reg[0] + reg[1])
 
     def all_reduce_nvls(self, group, byte_offset, dst, elems, dtype, scale=1.0, lane=LANE_ACT, stream=None):
         """In-switch all-reduce of ``elems`` values at ``byte_offset`` of the group's NVLS buffer -> ``dst`` (or in place)."""
@@ -363,14 +416,7 @@ class BgComm:
 
     # ---- groups ---------------------------------------------------------------------------------------
     def group_id(self, group):
-        ranks = tuple(group.ranks)
-        gid = self._gids.get(ranks)
-        if gid is None:
-            arr = (_i * len(ranks))(*ranks)
-            out = _i()
-            check(lib().bg_group_create(self._ctx, arr, len(ranks), ctypes.byref(out)))
-            gid = self._gids[ranks] = out.value
-        return gid
+        return self._gid_of_ranks(tuple(group.ranks))
 
     # ---- symmetric memory -----------------------------------------------------------------------------
     def alloc(self, nbytes):
@@ -423,14 +469,17 @@ class BgComm:
     # ---- collectives (async on the current or given torch stream) -------------------------------------
     @contextlib.contextmanager
     def _in_order(self, stream):
-        """Every kernel that waits on peers is launched in ONE total order per rank, whatever stream it is on: it first waits
-        (event) for the previous such kernel when that one went to another stream.  Two peer-waiting kernels running side by
-        side can each hold the registers the other needs on a different rank (A runs X and cannot place Y, B runs Y and
-        cannot place X) -- a cross-rank deadlock seen with ZeRO-3's concurrent all-gather and reduce-scatter at Llama-70B
-        sizes.  The program order is the same on every rank, so a single chain per rank is deadlock-free; kernels that do
-        not wait on peers (GEMMs, attention, elementwise) still overlap freely with the chain."""
+        """The stream a cross-rank kernel is launched on.  Round 1 chained every such kernel of a rank into one total order
+        (its 256-thread / 128-register kernels could not share an SM, and two of them in flight on different streams could
+        deadlock across ranks -- seen with ZeRO-3's concurrent all-gather and reduce-scatter at Llama-70B sizes).  The slim
+        kernels (128 threads x <= 64 registers, one CTA per SM, no shared memory) are always co-resident, beside each other
+        and beside a GEMM, so no ordering is imposed any more: collectives on different streams really overlap.
+        ``HGB_SERIAL_COLLECTIVES=1`` restores the chain (debugging aid)."""
         import torch
         s = torch.cuda.current_stream() if stream is None else stream
+        if not _SERIAL:
+            yield _vp(s.cuda_stream)
+            return
         last = self._last_coll
         if last is not None and last[0] != s.cuda_stream:
             s.wait_event(last[1])
@@ -505,6 +554,21 @@ class BgComm:
             check(lib().bg_gemm_reduce_scatter(self._ctx, self.group_id(group), lane, _ptr(a), _ptr(b), int(m), int(n), int(k), int(layout),
                                                partial.sub(partial_byte_offset), partial.sub(flags_byte_offset), _ptr(out),
                                                sp))
+
+    def gemm_all_reduce(self, group, a, b, m, n, k, layout, buf, partial_byte_offset, flags_byte_offset, out_byte_offset,
+                        lane=LANE_ACT, stream=None):
+        """C = A op B summed over ``group``, complete in every member's ``buf`` at ``out_byte_offset`` (GEMM + all-reduce fused)."""
+        with self._in_order(stream) as sp:
+            check(lib().bg_gemm_all_reduce(self._ctx, self.group_id(group), lane, _ptr(a), _ptr(b), int(m), int(n), int(k), int(layout),
+                                           buf.sub(partial_byte_offset), buf.sub(flags_byte_offset), buf.sub(out_byte_offset), sp))
+
+    def all_gather_gemm(self, group, a_local, b, out, m, n, k, layout, buf, stage_byte_offset, flags_byte_offset, comm_stream,
+                        lane=LANE_PUSH, stream=None):
+        """out[M,N] = gather_M(a_local) op B: chunk-signalled push on ``comm_stream`` + GEMM consuming chunks as they land."""
+        with self._in_order(stream) as sp:
+            check(lib().bg_all_gather_gemm(self._ctx, self.group_id(group), lane, _ptr(a_local), buf.sub(stage_byte_offset),
+                                           buf.sub(flags_byte_offset), _ptr(b), _ptr(out), int(m), int(n), int(k), int(layout), sp,
+                                           _vp(comm_stream.cuda_stream)))
 
     def p2p_send(self, peer_rank, dst_offset, src, flag_id, stream=None):
         check(lib().bg_p2p_send(self._ctx, int(peer_rank), int(dst_offset), _ptr(src), src.numel() * src.element_size(),

@@ -67,12 +67,23 @@ DEFAULTS = dict(
 )
 
 
+# options that are NOT defaults of the runtime but that model families / drivers legitimately attach to the namespace
+_EXTRA = {"model_size", "set_model_config_manually", "set_layernum_manually", "set_seqlen_manually", "vocab_size", "num_hidden_layers",
+          "kv_channels", "train_iters", "train_samples", "lr_decay_style", "lr_decay_iters", "lr_decay_samples", "lr_warmup_iters",
+          "lr_warmup_samples", "lr_warmup_fraction", "lr_warmup_init", "min_lr", "start_weight_decay", "end_weight_decay",
+          "weight_decay_incr_style", "use_checkpoint_opt_param_scheduler", "override_opt_param_scheduler", "num_layers",
+          "max_position_embeddings", "clip_grad", "layernorm_type", "activation", "add_bias", "position_embedding_type", "causal"}
+# explicit types of the options whose default is None (argparse would otherwise hand them over as strings)
+_NONE_TYPES = {"num_query_groups": int, "galvatron_config_path": str, "load": str, "save": str}
+
+
 def make_args(**overrides):
-    unknown = set(overrides) - set(DEFAULTS)
+    unknown = sorted(set(overrides) - set(DEFAULTS) - _EXTRA)
+    if unknown:
+        raise TypeError("unknown runtime argument(s) %s (a typo? known: the keys of arguments.DEFAULTS)" % ", ".join(unknown))
     ns = types.SimpleNamespace(**DEFAULTS)
     for k, v in overrides.items():
         setattr(ns, k, v)
-    ns._unknown = sorted(unknown)
     return ns
 
 
@@ -82,7 +93,7 @@ def parse_args(argv):
         if isinstance(v, bool):
             p.add_argument("--" + k, type=lambda s: s.lower() in ("1", "true", "yes"), default=v)
         elif v is None:
-            p.add_argument("--" + k, default=None)
+            p.add_argument("--" + k, type=_NONE_TYPES.get(k, str), default=None)
         else:
             p.add_argument("--" + k, type=type(v), default=v)
     p.add_argument("--no_async_grad_reduce", action="store_false", dest="async_grad_reduce")

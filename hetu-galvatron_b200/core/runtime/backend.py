@@ -64,21 +64,44 @@ class CudaBackend:
                     except RuntimeError:
                         arena_bytes = 0
                 arena_bytes = arena_bytes or (1 << 30)
-            # HGB_NVLS=1 (opt-in): arena from the virtual-memory API so that NVSwitch multicast objects can bind the activation
-            # staging buffers; large tensor-parallel all-reduces then reduce inside the switch
-            self.nvls = os.environ.get("HGB_NVLS", "0") == "1" and self.world > 1
-            comm = _bg.BgComm(self.rank, self.world, self.device_index, arena_bytes, vmm=self.nvls)
+            # NVLS (default on a multi-GPU job; HGB_NVLS=0 switches it off): the arena comes from the virtual-memory API so that
+            # NVSwitch multicast objects can bind it; collectives on multicast-bound buffers then reduce / replicate inside
+            # the switch above 1 MiB.  A driver or fabric without multicast keeps the cudaMalloc + cudaIpc arena.
+            self.nvls = os.environ.get("HGB_NVLS", "1") == "1" and self.world > 1
+            comm = None
+            if self.nvls:
+                try:
+                    comm = _bg.BgComm(self.rank, self.world, self.device_index, arena_bytes, vmm=True)
+                    if not comm.arena_mode()[1]:
+                        comm.close()
+                        comm = None
+                except _bg.BgError:
+                    comm = None
+                if self.world > 1:      # every rank must take the same decision (one box, one driver: it does; checked anyway)
+                    import torch.distributed as dist
+                    flags = [None] * self.world
+                    dist.all_gather_object(flags, comm is not None)
+                    if not all(flags):
+                        if comm is not None:
+                            comm.close()
+                        comm = None
+                self.nvls = comm is not None
+            if comm is None:
+                comm = _bg.BgComm(self.rank, self.world, self.device_index, arena_bytes, vmm=False)
             if self.world > 1:
                 comm.connect_vmm() if self.nvls else comm.connect_ipc()
-            if self.nvls and not comm.arena_mode()[1]:
-                self.nvls = False          # no multicast on this device / fabric: peer-to-peer kernels only
         self.comm = comm
         if os.environ.get("HGB_TIMEOUT_MS"):      # device-side barrier timeout (default 60 s): shorter for debugging runs
             _bg.set_tunable("timeout_ms", int(os.environ["HGB_TIMEOUT_MS"]))
         self.unshard_stream = torch.cuda.Stream(device=self.device)
         self.reduce_stream = torch.cuda.Stream(device=self.device)
         self.p2p_stream = torch.cuda.Stream(device=self.device)
+        self.comm_stream = torch.cuda.Stream(device=self.device)     # push kernels of the fused all-gather + GEMM; overlapped gathers
         self.fuse_gemm_rs = os.environ.get("HGB_FUSE_GEMM_RS", "1") != "0"
+        self.fuse_gemm_ar = os.environ.get("HGB_FUSE_GEMM_AR", "1") != "0"
+        self.fuse_ag_gemm = os.environ.get("HGB_FUSE_AG_GEMM", "1") != "0"
+        self.n_fused = {"gemm_rs": 0, "gemm_ar": 0, "ag_gemm": 0}
+        self.comm_profile = None   # bench.py: {kind: [(start_event, end_event, algorithmic_bus_bytes)]} while timing the collectives
         self.attn_impl = os.environ.get("HGB_ATTN", "cudnn")
         self._staging = {}  # group ranks -> SymBuffer
         self._scratch = {}
@@ -90,6 +113,12 @@ class CudaBackend:
             self.comm.close()
             self.comm = None
 
+    # ---- in-step timing of the collectives (bench.py path legs) ----------------------------------------------------
+    def _timed(self, kind, bus_bytes, stream=None):
+        """Context manager: when ``comm_profile`` is a dict, bracket the launch with CUDA events on its stream and record the
+        algorithmic bus bytes (nccl-tests convention: AG/RS/A2A (p-1)/p*N, AR 2(p-1)/p*N, p2p N) of the call."""
+        return _Timed(self, kind, bus_bytes, stream)
+
     # ---- memory -------------------------------------------------------------------------------------------
     def sym_alloc(self, group, nbytes):
         return self.comm.sym_alloc(group, nbytes)
@@ -98,8 +127,8 @@ class CudaBackend:
 
     def exchange(self):
         self.comm.exchange()
-        if getattr(self, "nvls", False) and self._staging:
-            self.comm.setup_nvls([buf for buf in self._staging.values() if buf.group.size > 1])
+        if getattr(self, "nvls", False):
+            self.nvls_regions = self.comm.setup_nvls()
 
     def reserve_staging(self, group, nbytes):
         """Per-group activation staging buffer (peer-visible).  Must be called (identically on all members) before
@@ -112,10 +141,12 @@ class CudaBackend:
         if cur is None or cur.data_bytes < nbytes:
             if cur is not None and cur.offsets is not None:
                 raise self.bg.BgError("staging buffer for group %s is %d B, need %d B (reserve before exchange())" % (key, cur.data_bytes, nbytes))
-            align = self.comm.arena_mode()[2] if getattr(self, "nvls", False) else 256
-            buf = self.comm.sym_alloc(group, nbytes + self.FLAG_BYTES, align=max(256, align))   # tail: per-tile arrival counters of the fused GEMM+RS
+            # three regions of `nbytes`: [0] general staging / all-gather landing, [1] partial tiles of the fused GEMM +
+            # reduce-scatter / all-reduce, [2] the all-reduce result every member broadcasts into; tail: arrival counters
+            # (first half: per-tile counters of the scattering GEMMs, second half: per-block counters of the gathering GEMM)
+            buf = self.comm.sym_alloc(group, 3 * nbytes + self.FLAG_BYTES)
             buf.data_bytes = nbytes
-            buf.u8[nbytes:].zero_()
+            buf.u8[3 * nbytes:].zero_()
             self._staging[key] = buf
         return self._staging[key]
 
@@ -155,8 +186,10 @@ class CudaBackend:
             if unit.dp_type == "ddp":
                 self.cast(unit.flat_param.data, unit.w_flat)
             else:
-                self.comm.all_gather_cast(unit.group, unit.flat_param.data, unit.W, shard_elems=unit.shard_elems,
-                                          lane=self.bg.LANE_UNSHARD, dst_dtype=unit.param_dtype)
+                d = unit.group.size
+                with self._timed("sdp_all_gather", (d - 1) / d * unit.padded * 2, self.unshard_stream):
+                    self.comm.all_gather_cast(unit.group, unit.flat_param.data, unit.W, shard_elems=unit.shard_elems,
+                                              lane=self.bg.LANE_UNSHARD, dst_dtype=unit.param_dtype)
             unit._unshard_event = torch.cuda.Event()
             unit._unshard_event.record(self.unshard_stream)
 
@@ -176,9 +209,11 @@ class CudaBackend:
         with torch.cuda.stream(self.reduce_stream):
             self.reduce_stream.wait_event(ev)
             if unit.dp_type != "ddp":
-                self.comm.reduce_scatter_acc(unit.group, unit.G, unit.reduce_dtype, unit.master_grad,
-                                             shard_elems=unit.shard_elems, prescale=1.0 / unit.prediv,
-                                             postscale=1.0 / unit.postdiv, accumulate=accumulate, lane=self.bg.LANE_REDUCE)
+                d, gsz = unit.group.size, (4 if unit.reduce_dtype == torch.float32 else 2)
+                with self._timed("sdp_reduce_scatter", (d - 1) / d * unit.padded * gsz, self.reduce_stream):
+                    self.comm.reduce_scatter_acc(unit.group, unit.G, unit.reduce_dtype, unit.master_grad,
+                                                 shard_elems=unit.shard_elems, prescale=1.0 / unit.prediv,
+                                                 postscale=1.0 / unit.postdiv, accumulate=accumulate, lane=self.bg.LANE_REDUCE)
             elif unit.group.size == 1:
                 self.cast(unit.g_flat, unit.master_grad, accumulate=accumulate)
             else:  # DDP layers: all-reduce of the full flat gradient (_runtime_utils.py:932-950), then cast/accumulate
@@ -197,9 +232,11 @@ class CudaBackend:
         ev.record(torch.cuda.current_stream())
         with torch.cuda.stream(self.reduce_stream):
             self.reduce_stream.wait_event(ev)
-            self.comm.reduce_scatter_adamw(unit.group, unit.G, unit.reduce_dtype, unit.flat_param.data, unit.exp_avg, unit.exp_avg_sq,
-                                           unit.shard_elems, 1.0 / unit.prediv, 1.0 / unit.postdiv, lr, b1, b2, eps, wd, step,
-                                           lane=self.bg.LANE_REDUCE)
+            d, gsz = unit.group.size, (4 if unit.reduce_dtype == torch.float32 else 2)
+            with self._timed("sdp_reduce_scatter_adamw", (d - 1) / d * unit.padded * gsz, self.reduce_stream):
+                self.comm.reduce_scatter_adamw(unit.group, unit.G, unit.reduce_dtype, unit.flat_param.data, unit.exp_avg, unit.exp_avg_sq,
+                                               unit.shard_elems, 1.0 / unit.prediv, 1.0 / unit.postdiv, lr, b1, b2, eps, wd, step,
+                                               lane=self.bg.LANE_REDUCE)
 
     def finish_reductions(self):
         torch.cuda.current_stream().wait_stream(self.reduce_stream)
@@ -264,13 +301,10 @@ class CudaBackend:
             return out
         buf, off = self._stage(x, group)
         out = torch.empty_like(x)
-        nbytes = x.numel() * x.element_size()
-        if (getattr(self, "nvls", False) and op == "sum" and nbytes >= self.NVLS_MIN_BYTES and self.comm.has_nvls(group)
-                and x.dtype in (torch.bfloat16, torch.float32)):
-            self.comm.all_reduce_nvls(group, off, out, x.numel(), x.dtype)       # reduced and replicated inside the NVSwitch
-            return out
-        self.comm.all_reduce(group, buf, out, elems=x.numel(), op=self.bg.MAX if op == "max" else self.bg.SUM,
-                             src_byte_offset=off)
+        # (above 1 MiB on a multicast-bound staging buffer the C side reduces and replicates inside the NVSwitch)
+        with self._timed("all_reduce", 2.0 * (group.size - 1) / group.size * x.numel() * x.element_size()):
+            self.comm.all_reduce(group, buf, out, elems=x.numel(), op=self.bg.MAX if op == "max" else self.bg.SUM,
+                                 src_byte_offset=off)
         return out
 
     def all_reduce_inplace(self, x, group):
@@ -281,9 +315,11 @@ class CudaBackend:
         buf = self._staging.get(tuple(group.ranks))
         nbytes = x.numel() * x.element_size()
         if (buf is None or not x.is_contiguous() or not self._is_staging(x, buf) or x.dtype not in (torch.bfloat16, torch.float32)
-                or nbytes < self.NVLS_MIN_BYTES or nbytes % 16):
+                or nbytes < self.NVLS_MIN_BYTES or nbytes % 16
+                or not self.comm.has_nvls(group, buf, x.data_ptr() - buf.u8.data_ptr(), nbytes)):
             return False
-        self.comm.all_reduce_nvls(group, x.data_ptr() - buf.u8.data_ptr(), None, x.numel(), x.dtype)
+        region = self.comm._nvls[tuple(group.ranks)]
+        self.comm.all_reduce_nvls(group, x.data_ptr() - self.comm.arena_ptr - region[0], None, x.numel(), x.dtype)
         return True
 
     def _all_reduce_padded(self, x, group, op, out):
@@ -307,19 +343,34 @@ class CudaBackend:
         out = torch.empty((n * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
         chunk = x.numel()
         self._check_vec(x, chunk)
-        self.comm.all_to_all_rows(group, [dict(src=buf, src_byte_offset=off, dst=out, batch=1, rows=1, row_elems=chunk,
-                                               src_bs=0, src_rs=0, src_me_off=0, dst_bs=0, dst_rs=0, dst_peer_off=chunk)], x.dtype)
+        with self._timed("all_gather", (n - 1) / n * out.numel() * out.element_size()):
+            self.comm.all_to_all_rows(group, [dict(src=buf, src_byte_offset=off, dst=out, batch=1, rows=1, row_elems=chunk,
+                                                   src_bs=0, src_rs=0, src_me_off=0, dst_bs=0, dst_rs=0, dst_peer_off=chunk)], x.dtype)
         return out
 
-    def all_gather_into_staging(self, x, group):
+    def all_gather_into_staging(self, x, group, overlap=False):
         """Push all-gather whose result stays in the group's staging buffer (operand of the next GEMM only):
-        the Megatron-SP gather of layers.py:399-413."""
+        the Megatron-SP gather of layers.py:399-413.  ``overlap``: launch it on the communication stream, ordered after the
+        work already in the current stream, and return (tensor, event) -- the caller runs independent work (the dgrad GEMM,
+        as layers.py:449-462 overlaps them) and waits for the event before touching the gathered tensor."""
         x = x.contiguous()
         n = group.size
         out, buf = self.staging_tensor(group, (n * x.shape[0],) + tuple(x.shape[1:]), x.dtype)
         self._check_vec(x, x.numel())
-        self.comm.all_gather_cast(group, x, buf, shard_elems=x.numel(), lane=self.bg.LANE_ACT, dst_dtype=x.dtype)
-        return out
+        bus = (n - 1) / n * out.numel() * out.element_size()
+        if not overlap:
+            with self._timed("all_gather", bus):
+                self.comm.all_gather_cast(group, x, buf, shard_elems=x.numel(), lane=self.bg.LANE_ACT, dst_dtype=x.dtype)
+            return out
+        cur = torch.cuda.current_stream()
+        self.comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comm_stream):
+            with self._timed("all_gather", bus, self.comm_stream):
+                self.comm.all_gather_cast(group, x, buf, shard_elems=x.numel(), lane=self.bg.LANE_PUSH, dst_dtype=x.dtype)
+            ev = torch.cuda.Event()
+            ev.record(self.comm_stream)
+        x.record_stream(self.comm_stream)
+        return out, ev
 
     def reduce_scatter_first_dim(self, x, group):
         """[n*s, ...] -> [s, ...] sum (mappings_group.py:105-122 _reduce_scatter_along_first_dim)."""
@@ -331,7 +382,8 @@ class CudaBackend:
         buf, off = self._stage(x, group)
         out = torch.empty((x.shape[0] // n,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
         self._check_vec(x, out.numel())
-        self.comm.reduce_scatter_acc(group, buf, x.dtype, out, shard_elems=out.numel(), lane=self.bg.LANE_ACT, src_byte_offset=off)
+        with self._timed("reduce_scatter", (n - 1) / n * x.numel() * x.element_size()):
+            self.comm.reduce_scatter_acc(group, buf, x.dtype, out, shard_elems=out.numel(), lane=self.bg.LANE_ACT, src_byte_offset=off)
         return out
 
     def all_gather_last_dim(self, x, group):
@@ -374,7 +426,8 @@ class CudaBackend:
                                   src_bs=s_in * n_in * d, src_rs=n_in * d, src_me_off=sl * n_in * d,
                                   dst_bs=sl * n_in * p * d, dst_rs=n_in * p * d, dst_peer_off=n_in * d))
             outs.append(out)
-        self.comm.all_to_all_rows(group, descs, tensors[0].dtype)
+        with self._timed("all_to_all", (p - 1) / p * sum(t.numel() * t.element_size() for t in tensors)):
+            self.comm.all_to_all_rows(group, descs, tensors[0].dtype)
         return outs
 
     # ---- math ops --------------------------------------------------------------------------------------------
@@ -413,7 +466,64 @@ class CudaBackend:
             return False
         buf = self._staging.get(tuple(group.ranks))
         tiles = (m // p // 128) * ((n + 255) // 256)
-        return buf is not None and buf.data_bytes >= m * n * 2 and tiles * 4 <= self.FLAG_BYTES
+        return buf is not None and buf.data_bytes >= m * n * 2 and tiles * 4 <= self.FLAG_BYTES // 2
+
+    FUSE_AR_MIN_K = 1024   # as FUSE_MIN_K, for the fused GEMM + all-reduce
+
+    @staticmethod
+    def _mnk(a, b, layout):
+        code = {"tn": 0, "nn": 1, "nt": 2}[layout]
+        if code == 2:
+            k_, m_ = a.shape
+        else:
+            m_, k_ = a.shape
+        return code, m_, (b.shape[0] if code == 0 else b.shape[1]), k_
+
+    def can_fuse_gemm_ar(self, m, n, group, k=None):
+        p = 1 if group is None else group.size
+        if not self.fuse_gemm_ar or p < 2 or m % (p * 128) or n % 8:
+            return False
+        if k is not None and k < self.FUSE_AR_MIN_K and os.environ.get("HGB_FUSE_GEMM_AR") != "force":
+            return False
+        buf = self._staging.get(tuple(group.ranks))
+        tiles = (m // p // 128) * ((n + 255) // 256)
+        return buf is not None and buf.data_bytes >= m * n * 2 and tiles * 4 <= self.FLAG_BYTES // 2 // 2
+
+    def gemm_all_reduce(self, a, b, layout, group):
+        """[M, N] = sum over ``group`` of A op B, on every member (GEMM + C5/C6 in one operation): partial tiles go to their
+        owner's HBM, the owner's tile reducer sums them as they land and broadcasts the rows into every member's result."""
+        code, m_, n_, k_ = self._mnk(a, b, layout)
+        buf = self.staging(group, m_ * n_ * 2)
+        r = buf.data_bytes
+        with self._timed("gemm_all_reduce", 2.0 * (group.size - 1) / group.size * m_ * n_ * 2):
+            self.comm.gemm_all_reduce(group, a, b, m_, n_, k_, code, buf, r, 3 * r, 2 * r)
+        self.n_fused["gemm_ar"] += 1
+        # the symmetric result buffer is rewritten by the next fused all-reduce of this group: hand out a private copy
+        return buf.u8[2 * r: 2 * r + m_ * n_ * 2].view(torch.bfloat16).view(m_, n_).clone()
+
+    def can_fuse_ag_gemm(self, m, k, group):
+        p = 1 if group is None else group.size
+        if not self.fuse_ag_gemm or p < 2 or m % (p * 128) or k % 8:
+            return False
+        buf = self._staging.get(tuple(group.ranks))
+        return buf is not None and buf.data_bytes >= m * k * 2 and (m // 128) * 4 <= self.FLAG_BYTES // 2
+
+    def all_gather_gemm(self, a_local, b, layout, group):
+        """out[M, N] = gather_rows(a_local[M/p, K]) op B (C7 + GEMM in one operation).  Returns (out, gathered A) -- the gathered
+        operand sits complete in the group's staging buffer afterwards (the wgrad GEMM of the same layer reads it there)."""
+        p = group.size
+        code = {"tn": 0, "nn": 1}[layout]
+        ml, k_ = a_local.shape
+        m_ = ml * p
+        n_ = b.shape[0] if code == 0 else b.shape[1]
+        buf = self.staging(group, m_ * k_ * 2)
+        out = torch.empty(m_, n_, dtype=torch.bfloat16, device=a_local.device)
+        with self._timed("all_gather_gemm", (p - 1) / p * m_ * k_ * 2):
+            self.comm.all_gather_gemm(group, a_local, b, out, m_, n_, k_, code, buf, 0, 3 * buf.data_bytes + self.FLAG_BYTES // 2,
+                                      self.comm_stream)
+        a_local.record_stream(self.comm_stream)
+        self.n_fused["ag_gemm"] += 1
+        return out, buf.u8[: m_ * k_ * 2].view(torch.bfloat16).view(m_, k_)
 
     def gemm_reduce_scatter(self, a, b, layout, group):
         """[M, N] = A op B, reduce-scattered along M over ``group`` -> [M/p, N]: the tcgen05 GEMM's epilogue stores each
@@ -426,8 +536,10 @@ class CudaBackend:
         n_ = b.shape[0] if code == 0 else b.shape[1]
         buf = self.staging(group, m_ * n_ * 2)
         out = torch.empty(m_ // group.size, n_, dtype=torch.bfloat16, device=a.device)
-        self.comm.gemm_reduce_scatter(group, a, b, m_, n_, k_, code, buf, 0, buf.data_bytes, out)
+        with self._timed("gemm_reduce_scatter", (group.size - 1) / group.size * m_ * n_ * 2):
+            self.comm.gemm_reduce_scatter(group, a, b, m_, n_, k_, code, buf, buf.data_bytes, 3 * buf.data_bytes, out)
         self.n_fused_gemm_rs = getattr(self, "n_fused_gemm_rs", 0) + 1
+        self.n_fused["gemm_rs"] += 1
         return out
 
     def rmsnorm_fwd(self, x, weight, eps):
@@ -551,6 +663,25 @@ class CudaBackend:
 
     def launch_count(self):
         return self.bg.launch_count()
+
+
+class _Timed:
+    def __init__(self, be, kind, bus_bytes, stream):
+        self.be, self.kind, self.bus_bytes, self.stream = be, kind, bus_bytes, stream
+
+    def __enter__(self):
+        prof = self.be.comm_profile
+        if prof is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record(self.stream or torch.cuda.current_stream())
+        return self
+
+    def __exit__(self, *exc):
+        prof = self.be.comm_profile
+        if prof is not None and exc[0] is None:
+            self.e1.record(self.stream or torch.cuda.current_stream())
+            prof.setdefault(self.kind, []).append((self.e0, self.e1, float(self.bus_bytes)))
+        return False
 
 
 def _vec(x):

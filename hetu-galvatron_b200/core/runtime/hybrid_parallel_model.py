@@ -212,4 +212,10 @@ def _reserve_activation_staging(be, args, info, hp_whole, hp_model, tp_groups, s
         for lst in (tp_groups, sp_groups, split_sep_groups, allgather_sep_groups, fused_ag_groups, fused_sp_groups, cp_groups or ()):
             if lst:
                 reserve(lst[i])
+    # the whole job as one group (gradient-norm all-reduce of clip_grad_norm, utils.py:124-133): one NVSwitch domain
+    if 1 < world <= 8:
+        from .comm_groups import CommGroup
+        be.world_group = CommGroup(list(range(world)))
+        if tuple(be.world_group.ranks) not in seen:
+            be.reserve_staging(be.world_group, 4096)
     hp_model.reserve_transport(max_mbs)

@@ -444,11 +444,19 @@ class _CheckpointFn(torch.autograd.Function):
     recompute inside backward -- under the backward unshard, so no third all-gather."""
 
     @staticmethod
-    def forward(ctx, wrapper, kwargs, *inputs):
+    def forward(ctx, wrapper, kwargs, anchor, *inputs):
+        # ``anchor``: an empty tensor that requires grad, so that this node is part of the graph (and its backward runs, producing
+        # the layer's PARAMETER gradients) even when no activation input requires grad (a checkpointed first layer).
         ctx.wrapper, ctx.kwargs = wrapper, kwargs
         ctx.save_for_backward(*[t for t in inputs if torch.is_tensor(t)])
         ctx.is_tensor = [torch.is_tensor(t) for t in inputs]
         ctx.others = [t for t in inputs if not torch.is_tensor(t)]
+        # dropout inside the layer must draw the same masks when it is recomputed (checkpoint_wrapper preserves the RNG state,
+        # torch/utils/checkpoint.py); only captured when dropout is on -- the random-data scripts run with 0
+        ctx.rng = None
+        if wrapper.preserve_rng:
+            dev = next((t.device for t in inputs if torch.is_tensor(t) and t.is_cuda), None)
+            ctx.rng = (torch.get_rng_state(), dev, torch.cuda.get_rng_state(dev) if dev is not None else None)
         with torch.no_grad():
             out = wrapper.module(*inputs, **kwargs)
         return out
@@ -466,13 +474,23 @@ class _CheckpointFn(torch.autograd.Function):
                 inputs.append(t)
             else:
                 inputs.append(others.pop(0))
+        if ctx.rng is not None:
+            cpu_state, dev, cuda_state = ctx.rng
+            now = (torch.get_rng_state(), torch.cuda.get_rng_state(dev) if dev is not None else None)
+            torch.set_rng_state(cpu_state)
+            if dev is not None:
+                torch.cuda.set_rng_state(cuda_state, dev)
         with torch.enable_grad():
             out = wrapper.module(*inputs, **ctx.kwargs)
+        if ctx.rng is not None:
+            torch.set_rng_state(now[0])
+            if dev is not None:
+                torch.cuda.set_rng_state(now[1], dev)
         outs = out if isinstance(out, (tuple, list)) else (out,)
         pairs = [(o, g) for o, g in zip(outs, grads) if torch.is_tensor(o) and o.requires_grad and g is not None]
         torch.autograd.backward([o for o, _ in pairs], [g for _, g in pairs])
         wrapper._post_backward()
-        return (None, None) + tuple(t.grad if torch.is_tensor(t) and t.requires_grad else None for t in inputs)
+        return (None, None, None) + tuple(t.grad if torch.is_tensor(t) and t.requires_grad else None for t in inputs)
 
 
 class DataParallelModule(nn.Module):
@@ -486,6 +504,12 @@ class DataParallelModule(nn.Module):
         self.prev_unit = None           # backward prefetch target
         self.sync_gradients = True      # set per microbatch by the schedule (PipelineParallel.set_last_batch)
         self._fired = True              # did _post_backward run during the current backward_step?
+        self._anchor = None
+        try:
+            from .arguments import get_args
+            self.preserve_rng = float(getattr(get_args(), "dropout_prob", 0.0)) > 0.0
+        except RuntimeError:
+            self.preserve_rng = False
 
     def _pre_backward(self):
         unit = self.unit
@@ -529,8 +553,9 @@ class DataParallelModule(nn.Module):
     def _forward(self, inputs, kwargs):
         grad_mode = torch.is_grad_enabled()
         if self.checkpoint and grad_mode:
-            # a dummy grad-requiring input keeps the node alive when no activation input requires grad
-            return _CheckpointFn.apply(self, kwargs, *inputs)
+            if self._anchor is None or self._anchor.device != self.unit.flat_param.device:
+                self._anchor = torch.empty(0, device=self.unit.flat_param.device, requires_grad=True)
+            return _CheckpointFn.apply(self, kwargs, self._anchor, *inputs)
         if grad_mode:
             float_in = [i for i, t in enumerate(inputs) if torch.is_tensor(t) and t.is_floating_point() and t.requires_grad]
             if float_in:

@@ -82,10 +82,24 @@ class _StageLink:
         peer_off = int(self.buf.offs()[self.peer_idx]) + slot * self.slot_bytes
         with torch.cuda.stream(be.p2p_stream):
             be.p2p_stream.wait_event(ev)
-            flat = torch.cat([t.reshape(-1).view(torch.uint8) for t in tensors]) if len(tensors) > 1 else tensors[0].contiguous()
+            if len(tensors) > 1:
+                # every tensor starts on a 16-byte boundary of the slot, so a mixed-dtype boundary (bf16 activations + an int64
+                # mask) unpacks with plain views on the other side
+                flat = torch.zeros(self._packed_bytes(tensors), dtype=torch.uint8, device=tensors[0].device)
+                off = 0
+                for t in tensors:
+                    nbytes = t.numel() * t.element_size()
+                    flat[off:off + nbytes].copy_(t.contiguous().reshape(-1).view(torch.uint8))
+                    off += (nbytes + 15) // 16 * 16
+            else:
+                flat = tensors[0].contiguous()
             flat.record_stream(be.p2p_stream)
             assert flat.numel() * flat.element_size() <= self.slot_bytes, "pipeline message larger than the reserved slot"
             be.comm.p2p_send(self.peer, peer_off, flat, self.send_flag_base + slot, stream=be.p2p_stream)
+
+    @staticmethod
+    def _packed_bytes(tensors):
+        return sum((t.numel() * t.element_size() + 15) // 16 * 16 for t in tensors)
 
     def recv(self, shapes, dtypes, requires_grad):
         """Wait for the peer's next message on the current stream and unpack it into fresh tensors."""
@@ -102,7 +116,7 @@ class _StageLink:
             if requires_grad and t.is_floating_point():
                 t.requires_grad_(True)
             outs.append(t)
-            off += nbytes
+            off += nbytes if len(shapes) == 1 else (nbytes + 15) // 16 * 16
         be.comm.p2p_release(self.peer, self.recv_flag_base + slot)
         return outs
 

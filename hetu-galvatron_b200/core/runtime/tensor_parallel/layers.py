@@ -57,21 +57,33 @@ def _write_wgrad(weight, dy2d, x2d):
     return None
 
 
+def _can(be, name, *args):
+    fn = getattr(be, name, None)
+    return bool(fn and fn(*args))
+
+
 class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
     """y = x W^T with the tensor/sequence-parallel communication of layers.py:375-547.
 
     sequence_parallel: all-gather x along dim 0 before the GEMM (:399-413), re-gather in backward (:449-455) and
         reduce-scatter dgrad (:488-494).
     allreduce_dgrad:   all-reduce dgrad over the TP group (what ``copy_to_tensor_model_parallel_region`` does in
-        backward, mappings_group.py:139) -- done here so the dgrad GEMM can write into the staging buffer.
-    out_staged:        write y into the staging buffer (it is about to be all-reduced / reduce-scattered).
+        backward, mappings_group.py:139).
+    allreduce_out:     all-reduce y over the TP group (row-parallel forward, :1110-1114; identity in backward).
+    reduce_scatter_out: reduce-scatter y along the sequence (row-parallel forward under Megatron-SP, :1109); backward gathers dy.
     recompute:         (opt-in, ``--recompute_activations``) instead of saving ``input`` for the wgrad GEMM, save what it was made
         from -- ("swiglu", gate_up) or ("rmsnorm", x, norm_weight, eps), tensors the producing op keeps anyway -- and redo that
         elementwise pass in backward: one layer then holds 352 MiB less at Llama-3-8B / seq 8192.
+
+    Every GEMM that has a collective next to it runs as ONE fused operation when the shapes allow (M a multiple of p x 128):
+      all-gather -> GEMM        ``backend.all_gather_gemm``      (C7: SP forward; the row-parallel dgrad under SP)
+      GEMM -> reduce-scatter    ``backend.gemm_reduce_scatter``  (C8: row-parallel forward under SP; the SP dgrad)
+      GEMM -> all-reduce        ``backend.gemm_all_reduce``      (C5: row-parallel forward; C6: column-parallel dgrad)
+    otherwise the GEMM writes into the group's peer-visible staging buffer and the stand-alone collective kernel follows.
     """
 
     @staticmethod
-    def forward(ctx, input, weight, sequence_parallel, allreduce_dgrad, out_staged, tp_group, reduce_scatter_out=False,
+    def forward(ctx, input, weight, sequence_parallel, allreduce_dgrad, allreduce_out, tp_group, reduce_scatter_out=False,
                 recompute_kind=None, recompute_eps=0.0, *recipe):
         be = get_backend()
         ctx.recompute = (recompute_kind, recompute_eps, len(recipe)) if recompute_kind else None
@@ -79,31 +91,43 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
             ctx.save_for_backward(weight, *recipe)
         else:
             ctx.save_for_backward(input, weight)
-        ctx.reduce_scatter_out = reduce_scatter_out and _size(tp_group) > 1
+        multi = _size(tp_group) > 1
+        ctx.tp_group = tp_group
+        ctx.reduce_scatter_out = reduce_scatter_out and multi
+        n_out = weight.shape[0]
         if ctx.reduce_scatter_out:
             # row-parallel forward under Megatron-SP (layers.py:1061-1109): GEMM + reduce-scatter along the sequence
-            ctx.sequence_parallel, ctx.allreduce_dgrad, ctx.tp_group = False, False, tp_group
+            ctx.sequence_parallel, ctx.allreduce_dgrad = False, False
             x2d = input.reshape(-1, input.shape[-1])
-            n_out = weight.shape[0]
-            if getattr(be, "can_fuse_gemm_rs", None) and be.can_fuse_gemm_rs(x2d.shape[0], n_out, tp_group, x2d.shape[1]):
+            if _can(be, "can_fuse_gemm_rs", x2d.shape[0], n_out, tp_group, x2d.shape[1]):
                 out = be.gemm_reduce_scatter(x2d, weight, "tn", tp_group)       # one fused operation
             else:
                 staged, _ = be.staging_tensor(tp_group, (x2d.shape[0], n_out), input.dtype)
                 be.gemm(x2d, weight, "tn", out=staged)
                 out = be.reduce_scatter_first_dim(staged, tp_group)
             return out.view(input.shape[0] // tp_group.size, *input.shape[1:-1], n_out)
-        ctx.sequence_parallel = sequence_parallel and _size(tp_group) > 1
-        ctx.allreduce_dgrad = allreduce_dgrad and _size(tp_group) > 1
-        ctx.tp_group = tp_group
-        total = be.all_gather_into_staging(input, tp_group) if ctx.sequence_parallel else input
-        x2d = total.reshape(-1, total.shape[-1])
-        n_out = weight.shape[0]
-        if out_staged and _size(tp_group) > 1 and not ctx.sequence_parallel:
-            out, _ = be.staging_tensor(tp_group, (x2d.shape[0], n_out), input.dtype)
-            be.gemm(x2d, weight, "tn", out=out)
+        ctx.sequence_parallel = sequence_parallel and multi
+        ctx.allreduce_dgrad = allreduce_dgrad and multi
+        if ctx.sequence_parallel:
+            x2d = input.reshape(-1, input.shape[-1])
+            full_shape = (input.shape[0] * tp_group.size,) + tuple(input.shape[1:-1])
+            if _can(be, "can_fuse_ag_gemm", x2d.shape[0] * tp_group.size, x2d.shape[1], tp_group):
+                out, _ = be.all_gather_gemm(x2d.contiguous(), weight, "tn", tp_group)   # gather and GEMM overlap block by block
+            else:
+                total = be.all_gather_into_staging(input, tp_group)
+                out = be.gemm(total.reshape(-1, total.shape[-1]), weight, "tn")
+            return out.view(*full_shape, n_out)
+        x2d = input.reshape(-1, input.shape[-1])
+        if allreduce_out and multi:
+            if _can(be, "can_fuse_gemm_ar", x2d.shape[0], n_out, tp_group, x2d.shape[1]):
+                out = be.gemm_all_reduce(x2d, weight, "tn", tp_group)            # GEMM + two-shot all-reduce, one operation
+            else:
+                staged, _ = be.staging_tensor(tp_group, (x2d.shape[0], n_out), input.dtype)
+                be.gemm(x2d, weight, "tn", out=staged)
+                out = be.all_reduce(staged, tp_group)
         else:
             out = be.gemm(x2d, weight, "tn")
-        return out.view(*total.shape[:-1], n_out)
+        return out.view(*input.shape[:-1], n_out)
 
     @staticmethod
     def backward(ctx, grad_output):
@@ -121,22 +145,43 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
             n_recipe = 0
             input, weight = ctx.saved_tensors
         group = ctx.tp_group
-        if ctx.reduce_scatter_out:   # backward of the reduce-scatter is an all-gather along the sequence (mappings_group.py:243-258)
-            grad_output = be.all_gather_first_dim(grad_output.contiguous(), group)
-        dy2d = grad_output.reshape(-1, grad_output.shape[-1])
+        k = weight.shape[1]
+        grad_input, dgrad_done, gather_event = None, False, None
+        if ctx.reduce_scatter_out:
+            # backward of the reduce-scatter is an all-gather along the sequence (mappings_group.py:243-258); the dgrad GEMM
+            # consumes the gathered dy block by block while it arrives, and the wgrad GEMM reads it from staging afterwards
+            dy_local = grad_output.reshape(-1, grad_output.shape[-1])
+            if ctx.needs_input_grad[0] and _can(be, "can_fuse_ag_gemm", dy_local.shape[0] * group.size, dy_local.shape[1], group):
+                gi, dy2d = be.all_gather_gemm(dy_local.contiguous(), weight, "nn", group)
+                grad_input = gi.view(grad_output.shape[0] * group.size, *grad_output.shape[1:-1], k)
+                dgrad_done = True
+            else:
+                grad_output = be.all_gather_first_dim(grad_output.contiguous(), group)
+                dy2d = grad_output.reshape(-1, grad_output.shape[-1])
+        else:
+            dy2d = grad_output.reshape(-1, grad_output.shape[-1])
         if not dy2d.is_contiguous():
             dy2d = dy2d.contiguous()
+        m = dy2d.shape[0]
+        fuse_rs = ctx.sequence_parallel and ctx.needs_input_grad[0] and _can(be, "can_fuse_gemm_rs", m, k, group, dy2d.shape[1])
+        total = input
+        if weight.requires_grad and ctx.sequence_parallel:
+            if fuse_rs and getattr(be, "comm_stream", None) is not None:
+                # the re-gather of the input (for wgrad) runs on the communication stream WHILE the fused dgrad GEMM +
+                # reduce-scatter runs here (layers.py:449-462 overlaps the same pair); wgrad waits for it below
+                total, gather_event = be.all_gather_into_staging(input, group, overlap=True)
+            else:
+                total = be.all_gather_into_staging(input, group)
         grad_weight = None
-        if weight.requires_grad:
-            total = be.all_gather_into_staging(input, group) if ctx.sequence_parallel else input
+        if weight.requires_grad and gather_event is None:
             grad_weight = _write_wgrad(weight, dy2d, total.reshape(-1, total.shape[-1]))
-        grad_input = None
-        if ctx.needs_input_grad[0]:
-            m, k = dy2d.shape[0], weight.shape[1]
-            if ctx.sequence_parallel and getattr(be, "can_fuse_gemm_rs", None) and be.can_fuse_gemm_rs(m, k, group, dy2d.shape[1]):
+        if ctx.needs_input_grad[0] and not dgrad_done:
+            if fuse_rs:
                 # dgrad GEMM + reduce-scatter along the sequence (layers.py:462,488-494) as one fused operation
                 out = be.gemm_reduce_scatter(dy2d, weight, "nn", group)
                 grad_input = out.view(grad_output.shape[0] // group.size, *grad_output.shape[1:-1], k)
+            elif ctx.allreduce_dgrad and _can(be, "can_fuse_gemm_ar", m, k, group, dy2d.shape[1]):
+                grad_input = be.gemm_all_reduce(dy2d, weight, "nn", group).view(*grad_output.shape[:-1], k)
             elif ctx.sequence_parallel or ctx.allreduce_dgrad:
                 staged, _ = be.staging_tensor(group, (m, k), dy2d.dtype)  # overwrites the gathered input: wgrad is done
                 be.gemm(dy2d, weight, "nn", out=staged)
@@ -147,40 +192,55 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
                     grad_input = be.all_reduce(staged.view(*full_shape), group)
             else:
                 grad_input = be.gemm(dy2d, weight, "nn").view(*grad_output.shape[:-1], k)
+        if gather_event is not None:
+            be.wait_event(gather_event)
+            grad_weight = _write_wgrad(weight, dy2d, total.reshape(-1, total.shape[-1]))
         return (grad_input, grad_weight, None, None, None, None, None, None, None) + (None,) * n_recipe
 
 
 def linear_with_grad_accumulation_and_async_allreduce(input, weight, bias=None, gradient_accumulation_fusion=False,
                                                       async_grad_allreduce=False, sequence_parallel=False, tp_group=None,
-                                                      out_staged=False, reduce_scatter_out=False, recompute=None):
+                                                      allreduce_out=False, reduce_scatter_out=False, recompute=None):
     """Same call shape as layers.py:550-648 (``async_grad_allreduce`` here means "all-reduce dgrad over tp_group").
     ``recompute``: None, ("swiglu", gate_up) or ("rmsnorm", x, norm_weight, eps) -- see the Function's docstring."""
     if recompute is None:
         out = LinearWithGradAccumulationAndAsyncCommunication.apply(input, weight, sequence_parallel, async_grad_allreduce,
-                                                                    out_staged, tp_group, reduce_scatter_out)
+                                                                    allreduce_out, tp_group, reduce_scatter_out)
     else:
         kind = recompute[0]
         eps = float(recompute[3]) if kind == "rmsnorm" else 0.0
         recipe = recompute[1:3] if kind == "rmsnorm" else recompute[1:2]
         out = LinearWithGradAccumulationAndAsyncCommunication.apply(input, weight, sequence_parallel, async_grad_allreduce,
-                                                                    out_staged, tp_group, reduce_scatter_out, kind, eps, *recipe)
+                                                                    allreduce_out, tp_group, reduce_scatter_out, kind, eps, *recipe)
     return out if bias is None else out + bias
+
+
+def mark_tensor_parallel(param):
+    """``set_tensor_model_parallel_attributes`` (layers.py:95-105): this parameter is a different slice on every rank of its
+    tensor-parallel group.  Parameters WITHOUT the mark (norm weights, the row-parallel bias) are replicas -- the gradient-norm
+    of ``clip_grad_norm`` counts them once (clip_grads.py:61-75 ``param_is_not_tensor_parallel_duplicate``)."""
+    setattr(param, "tensor_model_parallel", True)
+    return param
 
 
 class _ParallelLinearBase(nn.Module):
     def _make_weight(self, rows, cols, init_std, params_dtype, device):
-        self.weight = nn.Parameter(torch.empty(rows, cols, dtype=params_dtype, device=device))
+        self.weight = mark_tensor_parallel(nn.Parameter(torch.empty(rows, cols, dtype=params_dtype, device=device)))
         self.init_std = init_std
         if self.weight.device.type != "meta":
             self.reset_parameters()
 
     def reset_parameters(self):
-        """``colummn_row_reset_parameters`` (tensor_parallel/reset.py:10-17): N(0, init_method_std), zero bias."""
+        """``colummn_row_reset_parameters`` (tensor_parallel/reset.py:10-17): N(0, init_method_std), zero bias.
+        (Parameter attributes are set here as well as at construction: materialising a meta module makes new Parameter objects.)"""
         nn.init.normal_(self.weight, mean=0.0, std=self.init_std)
+        mark_tensor_parallel(self.weight)
         if getattr(self, "bias", None) is not None:
             nn.init.zeros_(self.bias)
             if isinstance(self, RowParallelLinear):
-                setattr(self.bias, "sequence_parallel", self.sequence_parallel)  # layers.py:1045 (survives meta materialisation)
+                setattr(self.bias, "sequence_parallel", self.sequence_parallel)  # layers.py:1045
+            else:
+                mark_tensor_parallel(self.bias)
 
 
 class ColumnParallelLinear(_ParallelLinearBase):
@@ -202,7 +262,7 @@ class ColumnParallelLinear(_ParallelLinearBase):
             init_std = getattr(config, "init_method_std", init_std)
         self._make_weight(self.output_size_per_partition, input_size, init_std, params_dtype, device)
         if bias:
-            self.bias = nn.Parameter(torch.zeros(self.output_size_per_partition, dtype=params_dtype, device=device))
+            self.bias = mark_tensor_parallel(nn.Parameter(torch.zeros(self.output_size_per_partition, dtype=params_dtype, device=device)))
         else:
             self.register_parameter("bias", None)
 
@@ -255,10 +315,11 @@ class RowParallelLinear(_ParallelLinearBase):
                 input_, self.weight, None, async_grad_allreduce=False, sequence_parallel=False, tp_group=self.tp_group,
                 reduce_scatter_out=True, recompute=recompute)
         else:
-            out_parallel = linear_with_grad_accumulation_and_async_allreduce(
+            # GEMM and the all-reduce of :1110-1114 (C5) are one operation; its backward is the identity, as
+            # reduce_from_tensor_model_parallel_region's is (mappings_group.py:142-156)
+            out = linear_with_grad_accumulation_and_async_allreduce(
                 input_, self.weight, None, async_grad_allreduce=False, sequence_parallel=False, tp_group=self.tp_group,
-                out_staged=True, recompute=recompute)
-            out = reduce_from_tensor_model_parallel_region_group(out_parallel, self.tp_group)     # :1114 (C5)
+                allreduce_out=True, recompute=recompute)
         if not self.skip_bias_add and self.bias is not None:
             out = out + self.bias
         return out, (self.bias if self.skip_bias_add else None)
@@ -313,12 +374,14 @@ class VocabParallelEmbedding(nn.Module):
         if config is not None:
             init_std = getattr(config, "init_method_std", init_std)
         self.init_std = init_std
-        self.weight = nn.Parameter(torch.empty(self.num_embeddings_per_partition, embedding_dim, dtype=params_dtype, device=device))
+        self.weight = mark_tensor_parallel(nn.Parameter(torch.empty(self.num_embeddings_per_partition, embedding_dim, dtype=params_dtype,
+                                                                    device=device)))
         if self.weight.device.type != "meta":
             self.reset_parameters()
 
     def reset_parameters(self):
         nn.init.normal_(self.weight, mean=0.0, std=self.init_std)
+        mark_tensor_parallel(self.weight)
 
     def forward(self, input_):
         masked = _size(self.tp_group) > 1

@@ -31,10 +31,13 @@ int fail(int code, const char* fmt, ...);
     } while (0)
 
 struct Tunables {
-    long long comm_ctas = 296;     // CTAs of a cross-rank kernel (<= BG_MAX_CHANNELS): 2 per SM, co-resident with a GEMM CTA
+    long long comm_ctas = 148;     // CTAs of a cross-rank kernel (<= BG_MAX_CHANNELS): ONE slim CTA (128 thr x <= 64 regs) per SM
     long long local_ctas = 148 * 8;  // CTAs of a purely local streaming kernel
     long long timeout_ms = 60000;  // device-side barrier timeout
     long long oneshot_bytes = 512 * 1024;
+    long long nvls_min_bytes = 1 << 20;  // below this the peer-to-peer kernels win (latency)
+    long long nvls_gather = 1;     // all-gather / broadcast stores go through the switch (multimem.st) when the buffer is multicast-bound
+    long long nvls_reduce = 1;     // reduce-scatter loads are reduced in the switch (multimem.ld_reduce) when the buffer is multicast-bound
 };
 extern Tunables g_tun;
 

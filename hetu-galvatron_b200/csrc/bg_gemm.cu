@@ -11,13 +11,9 @@
 //                     NN  C = A[M,K] * B[K,N]     (B MN-major: TMA boxes of 64 N-elements x 64 K-rows)
 //                     NT  C = A[K,M]^T * B[K,N]   (A, B MN-major)
 //   edges           : TMA zero-fills out-of-bounds loads and clips stores, so M, N, K only need to be multiples of 8.
-#include <cuda.h>
+#include <stdlib.h>
 
-#include <map>
-#include <mutex>
-#include <tuple>
-
-#include "bg_common.cuh"
+#include "bg_ctx.cuh"
 
 using namespace bg;
 
@@ -121,36 +117,74 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
 }
 
 struct TileCoord { int m, n; };
-__device__ __forceinline__ TileCoord tile_of(int t, int m_blocks, int n_blocks, int m_rot = 0) {
+// kMode: which collective is fused into the GEMM
+enum { kPlain = 0, kScatterMode = 1, kGatherMode = 2 };
+
+template <int kMode>
+struct FuseParams {};
+
+__device__ __forceinline__ TileCoord tile_of_virtual(int t, int m_blocks, int n_blocks) {
     const int per_group = kGroupM * n_blocks;
     const int g = t / per_group, first_m = g * kGroupM;
     const int rows = min(kGroupM, m_blocks - first_m);
     const int r = t - g * per_group;
-    int m = first_m + r % rows + m_rot;     // m_rot: fused scatter starts every rank on a different owner's rows
-    if (m >= m_blocks) m -= m_blocks;
-    return {m, r / rows};
+    return {first_m + r % rows, r / rows};
 }
 
 // Fused GEMM + reduce-scatter (C5/C8): instead of storing C locally, the epilogue TMA-stores every finished 128x256 partial
 // tile straight into the HBM of the rank that owns those rows (peer store over NVLink) and bumps that rank's per-tile
 // arrival counter; a small reducer kernel on the owner sums the p partials of a tile as soon as all have landed.  Transfer and
 // math overlap tile by tile; no NCCL, no separate collective pass over the full activation.
-template <bool kScatter>
-struct ScatterParams {};
 template <>
-struct ScatterParams<true> {
+struct FuseParams<kScatterMode> {
     CUtensorMap dst[BG_MAX_PEERS];      // owner o's partial buffer viewed as [p * rows_per_rank][N] (block r = source rank r)
     uint32_t* flags[BG_MAX_PEERS];      // owner o's arrival counters, one per local tile
     int p, me, rows_per_rank;
 };
 
-template <int kLayout, bool kScatter = false>
+// Fused all-gather + GEMM (C7): A[M,K] is the concatenation of the members' [M/p, K] shards.  The rank's own rows are read
+// from its local shard; every other 128-row block is read from the staging slot the owner's push kernel fills, as soon as that
+// block's arrival counter shows all pushing CTAs have delivered it.  Blocks are walked in arrival order: block c of slot me,
+// me+1, ..., me-1, then block c+1 of every slot, so the first sweep over N needs only the first block of every slot.
+template <>
+struct FuseParams<kGatherMode> {
+    CUtensorMap a_local;                // [M/p][K]
+    const uint32_t* flags;              // [p][blocks_per_rank] arrival counters in THIS rank's arena
+    uint32_t target;                    // CTAs of the push kernel
+    int p, me, blocks_per_rank;
+    unsigned long long timeout_ns;
+    int* err;
+};
+
+template <int kMode>
+__device__ __forceinline__ int map_m(int mv, int m_blocks, const FuseParams<kMode>& fp) {
+    if constexpr (kMode == kScatterMode) {
+        // rank r walks the owners in the order r+1, r+2, ..., r (ring schedule): every owner receives from ONE peer at a time
+        int m = mv + ((fp.me + 1) % fp.p) * (fp.rows_per_rank / BLOCK_M);
+        return m >= m_blocks ? m - m_blocks : m;
+    } else if constexpr (kMode == kGatherMode) {
+        const int c = mv / fp.p, k = mv - c * fp.p;
+        int slot = fp.me + k; if (slot >= fp.p) slot -= fp.p;
+        return slot * fp.blocks_per_rank + c;
+    } else {
+        return mv;
+    }
+}
+template <int kMode>
+__device__ __forceinline__ TileCoord tile_of(int t, int m_blocks, int n_blocks, const FuseParams<kMode>& fp) {
+    TileCoord tc = tile_of_virtual(t, m_blocks, n_blocks);
+    tc.m = map_m<kMode>(tc.m, m_blocks, fp);
+    return tc;
+}
+
+template <int kLayout, int kMode = kPlain>
 __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b,
                                                                 const __grid_constant__ CUtensorMap map_c,
                                                                 const __nv_bfloat16* __restrict__ c_old, int M, int N, int K,
                                                                 int accumulate,
-                                                                const __grid_constant__ ScatterParams<kScatter> sp) {
+                                                                const __grid_constant__ FuseParams<kMode> sp) {
+    constexpr bool kScatter = kMode == kScatterMode, kGather = kMode == kGatherMode;
     constexpr bool kAMn = kLayout == kNT, kBMn = kLayout != kTN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -166,11 +200,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_con
     const int m_blocks = (M + BLOCK_M - 1) / BLOCK_M, n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
     const int num_tiles = m_blocks * n_blocks, k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
 
-    // Fused scatter: rank r walks the owners in the order r+1, r+2, ..., r (ring schedule), so at any moment every owner
+    // Fused scatter: rank r walks the owners in the order r+1, r+2, ..., r (ring schedule, map_m), so at any moment every owner
     // receives from ONE peer instead of all p-1 at once (incast would serialise the job on one GPU's NVLink ingress), and
     // the rank's own rows -- which need no NVLink -- come last, when the links are draining.
-    int m_rot = 0;
-    if constexpr (kScatter) m_rot = ((sp.me + 1) % sp.p) * (sp.rows_per_rank / BLOCK_M);
     if constexpr (kScatter) {
         // Programmatic dependent launch: the tile reducer (next kernel in this stream) may be scheduled once EVERY CTA of
         // this grid is running.  It spins on tiles this grid (and the peers') produce, so it must never take an SM's
@@ -201,7 +233,33 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_con
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const TileCoord tc = tile_of(t, m_blocks, n_blocks, m_rot);
+                const TileCoord tc = tile_of<kMode>(t, m_blocks, n_blocks, sp);
+                const CUtensorMap* amap = &map_a;
+                int a_row = tc.m * BLOCK_M;
+                if constexpr (kGather) {
+                    const int slot = tc.m / sp.blocks_per_rank, c = tc.m - slot * sp.blocks_per_rank;
+                    if (slot == sp.me) {
+                        amap = &sp.a_local; a_row = c * BLOCK_M;          // own rows: straight from the local shard
+                    } else {
+                        // the owner's push kernel counts this 128-row block in once per pushing CTA
+                        const uint32_t* f = sp.flags + slot * sp.blocks_per_rank + c;
+                        unsigned long long t0 = 0; unsigned spins = 0;
+                        while (true) {
+                            uint32_t v;
+                            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                            if (v >= sp.target) break;
+                            if ((++spins & 0x3ff) == 0) {
+                                unsigned long long now = gtimer();
+                                if (t0 == 0) t0 = now;
+                                else if (now - t0 > sp.timeout_ns) {
+                                    if (atomicCAS(sp.err + 1, 0, 4) == 0) { sp.err[2] = (int)blockIdx.x; sp.err[3] = tc.m; sp.err[4] = (int)v; sp.err[5] = (int)sp.target; sp.err[6] = slot; }
+                                    *sp.err = BG_ETIMEOUT; __threadfence_system(); __trap();
+                                }
+                            }
+                        }
+                        asm volatile("fence.proxy.async.global;" ::: "memory");   // the peer's stores (generic proxy) before my TMA reads (async proxy)
+                    }
+                }
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
                     const uint32_t bar = smem_u32(full_bar + stage);
@@ -211,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_con
 #pragma unroll
                         for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_2d(sa + j * (BLOCK_K * 128), &map_a, bar, tc.m * BLOCK_M + j * 64, kb * BLOCK_K);
                     } else {     // A stored [M][K]: one box of 64 K-elements x 128 rows
-                        tma_load_2d(sa, &map_a, bar, kb * BLOCK_K, tc.m * BLOCK_M);
+                        tma_load_2d(sa, amap, bar, kb * BLOCK_K, a_row);
                     }
                     if (kBMn) {
 #pragma unroll
@@ -263,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_con
         int buf = 0;
         uint32_t* prev_flag = nullptr;                // fused scatter: arrival counter of the tile whose stores are in flight
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            const TileCoord tc = tile_of(t, m_blocks, n_blocks, m_rot);
+            const TileCoord tc = tile_of<kMode>(t, m_blocks, n_blocks, sp);
             mbar_wait(smem_u32(tmem_full + acc), acc_phase);
             tc_fence_after();
 #pragma unroll 1
@@ -399,6 +457,34 @@ int g_num_sms = 0;
 
 }  // namespace
 
+int bg_preload_gemm();
+
+static int gemm_setup() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        BG_CUDA(cudaGetDevice(&dev));
+        int sms = 0;
+        BG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+#define BG_SMEM(K) BG_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes))
+        BG_SMEM(gemm_bf16_kernel<kTN>); BG_SMEM(gemm_bf16_kernel<kNN>); BG_SMEM(gemm_bf16_kernel<kNT>);
+        BG_SMEM((gemm_bf16_kernel<kTN, kScatterMode>)); BG_SMEM((gemm_bf16_kernel<kNN, kScatterMode>)); BG_SMEM((gemm_bf16_kernel<kNT, kScatterMode>));
+        BG_SMEM((gemm_bf16_kernel<kTN, kGatherMode>)); BG_SMEM((gemm_bf16_kernel<kNN, kGatherMode>));
+#undef BG_SMEM
+        g_num_sms = sms;
+    }
+    return BG_OK;
+}
+
+
+
+static int make_ab_maps(CUtensorMap* ma, CUtensorMap* mb, const void* a, const void* b, long long m, long long n, long long k, int layout) {
+    // A: TN/NN stored [M][K] (K-major: box 64 K x 128 rows); NT stored [K][M] (MN-major: box 64 M x 64 K-rows)
+    int rc = layout == kNT ? make_map(ma, a, k, m, 64, BLOCK_K) : make_map(ma, a, m, k, BLOCK_K, BLOCK_M);
+    if (rc) return rc;
+    // B: TN stored [N][K] (box 64 K x 256 rows); NN/NT stored [K][N] (box 64 N x 64 K-rows)
+    return layout == kTN ? make_map(mb, b, n, k, BLOCK_K, BLOCK_N) : make_map(mb, b, k, n, 64, BLOCK_K);
+}
+
 extern "C" int bg_gemm_bf16(const void* a, const void* b, void* c, long long m, long long n, long long k, int layout,
                             int accumulate, void* stream) {
     if (layout < 0 || layout > 2) return fail(BG_EINVAL, "bg_gemm_bf16: layout %d", layout);
@@ -406,28 +492,17 @@ extern "C" int bg_gemm_bf16(const void* a, const void* b, void* c, long long m, 
         return fail(BG_EINVAL, "bg_gemm_bf16: m,n,k (%lld,%lld,%lld) must be positive multiples of 8", m, n, k);
     if (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) % 16) return fail(BG_EINVAL, "bg_gemm_bf16: pointers must be 16-B aligned");
     CUtensorMap ma, mb, mc;
-    int rc;
-    // A: TN/NN stored [M][K] (K-major: box 64 K x 128 rows); NT stored [K][M] (MN-major: box 64 M x 64 K-rows)
-    rc = layout == kNT ? make_map(&ma, a, k, m, 64, BLOCK_K) : make_map(&ma, a, m, k, BLOCK_K, BLOCK_M);
-    if (rc) return rc;
-    // B: TN stored [N][K] (box 64 K x 256 rows); NN/NT stored [K][N] (box 64 N x 64 K-rows)
-    rc = layout == kTN ? make_map(&mb, b, n, k, BLOCK_K, BLOCK_N) : make_map(&mb, b, k, n, 64, BLOCK_K);
+    int rc = make_ab_maps(&ma, &mb, a, b, m, n, k, layout);
     if (rc) return rc;
     rc = make_map(&mc, c, m, n, kStoreCols, BLOCK_M);
     if (rc) return rc;
-    if (g_num_sms == 0) {
-        int dev = 0;
-        BG_CUDA(cudaGetDevice(&dev));
-        BG_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-        BG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kTN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        BG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        BG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    }
+    rc = gemm_setup();
+    if (rc) return rc;
     const long long tiles = ((m + BLOCK_M - 1) / BLOCK_M) * ((n + BLOCK_N - 1) / BLOCK_N);
     const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
     cudaStream_t st = (cudaStream_t)stream;
     const __nv_bfloat16* c_old = (const __nv_bfloat16*)c;
-    ScatterParams<false> none;
+    FuseParams<kPlain> none;
     if (layout == kTN) gemm_bf16_kernel<kTN><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, c_old, (int)m, (int)n, (int)k, accumulate, none);
     else if (layout == kNN) gemm_bf16_kernel<kNN><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, c_old, (int)m, (int)n, (int)k, accumulate, none);
     else gemm_bf16_kernel<kNT><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, c_old, (int)m, (int)n, (int)k, accumulate, none);
@@ -435,19 +510,27 @@ extern "C" int bg_gemm_bf16(const void* a, const void* b, void* c, long long m, 
     return BG_OK;
 }
 
-// ---- fused GEMM + reduce-scatter -------------------------------------------------------------------------------------------
+// ---- fused GEMM + reduce-scatter / all-reduce ---------------------------------------------------------------------------------
 namespace {
 
-__device__ __forceinline__ unsigned long long gtimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
+struct Bcast {
+    char* out[BG_MAX_PEERS];     // every member's full [M][N] output (all-reduce), or all null (reduce-scatter)
+    char* mc;                    // multicast address of that buffer (one multimem.st reaches every member), or null
+    int on;
+};
+
+__device__ __forceinline__ void mm_st_16g(void* mc, const uint4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
 }
 
-// One CTA per local tile (grid-strided): wait until all p partial tiles have landed, sum them in fp32, write bf16.
-__global__ void __launch_bounds__(256, 2) tile_reduce_kernel(const __nv_bfloat16* __restrict__ partial, uint32_t* __restrict__ flags,
-                                                          __nv_bfloat16* __restrict__ out, int p, int rows_per_rank, int N,
-                                                          int n_blocks, int local_tiles, unsigned long long timeout_ns, int* err) {
+// One CTA per local tile (grid-strided): wait until all p partial tiles have landed, sum them in fp32, write bf16 -- into the
+// local [M/p][N] result (reduce-scatter) or into rows [me*M/p, ...) of EVERY member's [M][N] result (all-reduce: the second
+// shot of the two-shot algorithm happens here, tile by tile, while the GEMMs are still producing).
+__global__ void __launch_bounds__(128, 8) tile_reduce_kernel(const __nv_bfloat16* __restrict__ partial, uint32_t* __restrict__ flags,
+                                                          __nv_bfloat16* __restrict__ out, int p, int me, int rows_per_rank, int N,
+                                                          int n_blocks, int local_tiles, const __grid_constant__ Bcast bc,
+                                                          unsigned long long timeout_ns, int* err) {
     for (int lt = blockIdx.x; lt < local_tiles; lt += gridDim.x) {
         if (threadIdx.x == 0) {
             unsigned long long t0 = 0;
@@ -457,9 +540,9 @@ __global__ void __launch_bounds__(256, 2) tile_reduce_kernel(const __nv_bfloat16
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + lt) : "memory");
                 if (v >= (uint32_t)p) break;
                 if ((++spins & 0x3ff) == 0) {
-                    unsigned long long now = gtimer_ns();
+                    unsigned long long now = gtimer();
                     if (t0 == 0) t0 = now;
-                    else if (now - t0 > timeout_ns) {
+                    else if (now - t0 > timeout_ns / 2) {     // (half: a missing tile is reported before the peers' barriers time out)
                         if (atomicCAS(err + 1, 0, 3) == 0) { err[2] = (int)blockIdx.x; err[3] = lt; err[4] = (int)v; err[5] = p; err[6] = local_tiles; }
                         *err = BG_ETIMEOUT; __threadfence_system(); __trap();
                     }
@@ -489,71 +572,113 @@ __global__ void __launch_bounds__(256, 2) tile_reduce_kernel(const __nv_bfloat16
 #pragma unroll
                     for (int e = 0; e < 8; ++e) acc[e] += f[e];
                 }
-            st16(out + off, pack8(acc));
+            const uint4 o = pack8(acc);
+            if (bc.on) {
+                const size_t goff = ((size_t)me * rows_per_rank * N + off) * 2;
+                if (bc.mc != nullptr) {
+                    mm_st_16g(bc.mc + goff, o);
+                } else {
+                    for (int k = 0; k < p; ++k) {
+                        int q = me + k; if (q >= p) q -= p;
+                        st16(bc.out[q] + goff, o);
+                    }
+                }
+            } else {
+                st16(out + off, o);
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) flags[lt] = 0;   // ready for the next use (peers only write again after the next entry barrier)
     }
+    // (all-reduce: the cross-rank exit barrier is the next kernel of the stream, bg_coll.cu)
+    // programmatic dependent of the GEMM: do not complete (and release the stream) before the GEMM grid has
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 }  // namespace
 
-// Internal entry used by bg_comm.cu (which owns contexts, groups and peer pointers).  partial/flags: per-member pointers.
+// Internal entry used by bg_coll.cu (which owns contexts, groups and peer pointers).  partial/flags: per-member pointers.
 // Both kernels go to ONE stream: the GEMM, then the reducer as its programmatic dependent (it starts when all GEMM CTAs are
-// resident, not when they finish, and never calls griddepcontrol.wait -- tiles are handed over through the arrival counters).
+// resident, not when they finish; tiles are handed over through the arrival counters).
 int bg_gemm_scatter_launch(const void* a, const void* b, long long m, long long n, long long k, int layout, int p, int me,
-                           void* const* partial_ptrs, uint32_t* const* flag_ptrs, void* out, unsigned long long timeout_ns,
-                           int* err_dev, cudaStream_t st) {
+                           void* const* partial_ptrs, uint32_t* const* flag_ptrs, void* out, void* const* bcast_ptrs, char* bcast_mc,
+                           unsigned long long timeout_ns, int* err_dev, cudaStream_t st) {
     if (layout < 0 || layout > 2) return fail(BG_EINVAL, "bg_gemm_reduce_scatter: layout %d", layout);
     if (m <= 0 || n <= 0 || k <= 0 || n % 8 || k % 8) return fail(BG_EINVAL, "bg_gemm_reduce_scatter: bad dims");
     if (m % ((long long)p * BLOCK_M)) return fail(BG_EINVAL, "bg_gemm_reduce_scatter: M=%lld must be a multiple of p*%d", m, BLOCK_M);
     const int rows_per_rank = (int)(m / p);
     CUtensorMap ma, mb;
-    int rc = layout == kNT ? make_map(&ma, a, k, m, 64, BLOCK_K) : make_map(&ma, a, m, k, BLOCK_K, BLOCK_M);
+    int rc = make_ab_maps(&ma, &mb, a, b, m, n, k, layout);
     if (rc) return rc;
-    rc = layout == kTN ? make_map(&mb, b, n, k, BLOCK_K, BLOCK_N) : make_map(&mb, b, k, n, 64, BLOCK_K);
-    if (rc) return rc;
-    ScatterParams<true> sp;
+    FuseParams<kScatterMode> sp;
     sp.p = p; sp.me = me; sp.rows_per_rank = rows_per_rank;
     for (int i = 0; i < BG_MAX_PEERS; ++i) {
         sp.flags[i] = i < p ? flag_ptrs[i] : nullptr;
         if (i < p) { rc = make_map(&sp.dst[i], partial_ptrs[i], (long long)p * rows_per_rank, n, kStoreCols, BLOCK_M); if (rc) return rc; }
         else sp.dst[i] = sp.dst[0];
     }
-    if (g_num_sms == 0) {
-        int dev = 0;
-        BG_CUDA(cudaGetDevice(&dev));
-        BG_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-        BG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kTN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        BG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        BG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    }
-    static bool scatter_attr = false;
-    if (!scatter_attr) {
-        BG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kTN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        BG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kNN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        BG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kNT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        scatter_attr = true;
-    }
+    rc = gemm_setup();
+    if (rc) return rc;
     const int m_blocks = (int)((m + BLOCK_M - 1) / BLOCK_M), n_blocks = (int)((n + BLOCK_N - 1) / BLOCK_N);
     const long long tiles = (long long)m_blocks * n_blocks;
     const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
     const int local_tiles = (rows_per_rank / BLOCK_M) * n_blocks;
     const CUtensorMap& mc_unused = sp.dst[0];
-    if (layout == kTN) gemm_bf16_kernel<kTN, true><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc_unused, nullptr, (int)m, (int)n, (int)k, 0, sp);
-    else if (layout == kNN) gemm_bf16_kernel<kNN, true><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc_unused, nullptr, (int)m, (int)n, (int)k, 0, sp);
-    else gemm_bf16_kernel<kNT, true><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc_unused, nullptr, (int)m, (int)n, (int)k, 0, sp);
+    if (layout == kTN) gemm_bf16_kernel<kTN, kScatterMode><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc_unused, nullptr, (int)m, (int)n, (int)k, 0, sp);
+    else if (layout == kNN) gemm_bf16_kernel<kNN, kScatterMode><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc_unused, nullptr, (int)m, (int)n, (int)k, 0, sp);
+    else gemm_bf16_kernel<kNT, kScatterMode><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc_unused, nullptr, (int)m, (int)n, (int)k, 0, sp);
     BG_CHECK_LAUNCH();
     // one reducer CTA fits beside a GEMM CTA (registers); more CTAs than SMs only queue
     const int rgrid = local_tiles < g_num_sms ? local_tiles : g_num_sms;
+    Bcast bc = {};
+    if (bcast_ptrs != nullptr) {
+        bc.on = 1; bc.mc = bcast_mc;
+        for (int i = 0; i < p; ++i) bc.out[i] = (char*)bcast_ptrs[i];
+    }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)rgrid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cfg.gridDim = dim3((unsigned)rgrid); cfg.blockDim = dim3(128);   // slim: fits beside the GEMM CTA and two more collectives cfg.dynamicSmemBytes = 0; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    static const bool no_pdl = getenv("HGB_NO_PDL") != nullptr;      // debugging aid: launch the reducer as an ordinary kernel
+    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
     BG_CUDA(cudaLaunchKernelEx(&cfg, tile_reduce_kernel, (const __nv_bfloat16*)partial_ptrs[me], (uint32_t*)flag_ptrs[me],
-                               (__nv_bfloat16*)out, p, rows_per_rank, (int)n, n_blocks, local_tiles, timeout_ns, err_dev));
+                               (__nv_bfloat16*)out, p, me, rows_per_rank, (int)n, n_blocks, local_tiles, bc, timeout_ns, err_dev));
     bg::g_launches.fetch_add(1, std::memory_order_relaxed);
+    return BG_OK;
+}
+
+// Fused all-gather + GEMM: the consumer half (the push kernel is launched by bg_coll.cu on the communication stream).
+int bg_gemm_gather_launch(const void* a_local, const void* a_staged, const void* b, void* c, long long m, long long n, long long k,
+                          int layout, int p, int me, const uint32_t* flags, uint32_t target, unsigned long long timeout_ns, int* err_dev,
+                          cudaStream_t st) {
+    if (layout != kTN && layout != kNN) return fail(BG_EINVAL, "bg_all_gather_gemm: layout %d", layout);
+    if (((uintptr_t)a_local | (uintptr_t)a_staged | (uintptr_t)b | (uintptr_t)c) % 16) return fail(BG_EINVAL, "bg_all_gather_gemm: pointers must be 16-B aligned");
+    CUtensorMap ma, mb, mc;
+    int rc = make_ab_maps(&ma, &mb, a_staged, b, m, n, k, layout);
+    if (rc) return rc;
+    rc = make_map(&mc, c, m, n, kStoreCols, BLOCK_M);
+    if (rc) return rc;
+    FuseParams<kGatherMode> gp;
+    rc = make_map(&gp.a_local, a_local, m / p, k, BLOCK_K, BLOCK_M);
+    if (rc) return rc;
+    gp.flags = flags; gp.target = target; gp.p = p; gp.me = me; gp.blocks_per_rank = (int)(m / p / BLOCK_M);
+    gp.timeout_ns = timeout_ns; gp.err = err_dev;
+    rc = gemm_setup();
+    if (rc) return rc;
+    const long long tiles = (m / BLOCK_M) * ((n + BLOCK_N - 1) / BLOCK_N);
+    const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+    if (layout == kTN) gemm_bf16_kernel<kTN, kGatherMode><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, nullptr, (int)m, (int)n, (int)k, 0, gp);
+    else gemm_bf16_kernel<kNN, kGatherMode><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, nullptr, (int)m, (int)n, (int)k, 0, gp);
+    BG_CHECK_LAUNCH();
+    return BG_OK;
+}
+
+// loads every kernel of this file and sets the dynamic shared-memory limits (see bg_preload_coll in bg_coll.cu)
+int bg_preload_gemm() {
+    int rc = gemm_setup();
+    if (rc) return rc;
+    cudaFuncAttributes attr;
+    BG_CUDA(cudaFuncGetAttributes(&attr, reinterpret_cast<const void*>(&tile_reduce_kernel)));
     return BG_OK;
 }

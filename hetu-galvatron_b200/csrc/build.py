@@ -10,8 +10,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["bg_comm.cu", "bg_ops.cu", "bg_gemm.cu"]
-HEADERS = ["bg_common.cuh", os.path.join(ROOT, "include", "bg_galvatron.h")]
+SOURCES = ["bg_comm.cu", "bg_coll.cu", "bg_ops.cu", "bg_gemm.cu"]
+HEADERS = ["bg_common.cuh", "bg_ctx.cuh", os.path.join(ROOT, "include", "bg_galvatron.h")]
 LIB = os.path.join(HERE, "libbg_galvatron.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-I" + os.path.join(ROOT, "include")]

@@ -155,8 +155,7 @@ def save_llama_module(save_path, model, optimizer, opt_param_scheduler, iter_num
         full = be.gather_master(unit)                      # collective over the unit's group: every member calls it
         if unit.group.size > 1 and unit.group.rank_in_group(rank) != 0:
             continue
-        inner = _wrapped_block(block.module)
-        prefix = _prefix_of(block.module, inner)
+        inner, prefix = _wrapped_block(block.module)
         state = {}
         for pname, tensor in unit.named_slices(full).items():
             key = pname[len(prefix):] if prefix and pname.startswith(prefix) else pname
@@ -165,18 +164,28 @@ def save_llama_module(save_path, model, optimizer, opt_param_scheduler, iter_num
         sub = first.rsplit(".", 1)[0]
         target = os.path.join(root, _dir_of(sub, inner))
         os.makedirs(target, exist_ok=True)
-        torch.save(state, os.path.join(target, "%d.pt" % _tp(unit.tp_group, rank)[0]))
+        _atomic_save(state, os.path.join(target, "%d.pt" % _tp(unit.tp_group, rank)[0]))
     os.makedirs(os.path.join(root, "optimizer"), exist_ok=True)
-    torch.save(optimizer.state_dict() if optimizer is not None else {}, os.path.join(root, "optimizer", "%d.pt" % rank))
+    _atomic_save(optimizer.state_dict() if optimizer is not None else {}, os.path.join(root, "optimizer", "%d.pt" % rank))
     be.barrier_all()
 
 
+def _atomic_save(obj, path):
+    """Write next to the target and rename: a failure never leaves a truncated file under the final name."""
+    tmp = "%s.tmp.%d" % (path, os.getpid())
+    torch.save(obj, tmp)
+    os.replace(tmp, path)
+
+
 def _wrapped_block(module):
-    """The block the reference wraps (and names checkpoint keys relative to): the decoder layer inside ``LlamaLayers_``,
-    the module itself for embedding / final norm / head."""
+    """-> (block, key prefix).  The block the reference wraps (and names checkpoint keys relative to): the decoder layer inside
+    ``LlamaLayers_``, the module itself for embedding / final norm / head.  A row whose (tp|sp, cp) differs from its
+    predecessor's is wrapped in ``Module_with_relocation`` (one ``module.`` level per wrapper, parallel.py:279-313): the
+    reference names keys relative to the FSDP-wrapped block, so the wrappers are transparent."""
+    prefix = ""
+    while hasattr(module, "groups") and hasattr(module, "module"):      # Module_with_relocation
+        module, prefix = module.module, prefix + "module."
     inner = getattr(module, "layer", None)
-    return inner if inner is not None and hasattr(inner, "idx") else module
-
-
-def _prefix_of(module, inner):
-    return "layer." if inner is not module else ""
+    if inner is not None and hasattr(inner, "idx"):
+        return inner, prefix + "layer."
+    return module, prefix

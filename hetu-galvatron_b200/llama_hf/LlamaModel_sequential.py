@@ -83,6 +83,7 @@ class LlamaLoss_(nn.Module):
 
     def reset_parameters(self):
         nn.init.normal_(self.weight, mean=0.0, std=self.init_std)
+        setattr(self.weight, "tensor_model_parallel", True)      # a column-parallel slice (layers.py:95-105)
 
     def forward(self, hidden_states):
         return linear_with_grad_accumulation_and_async_allreduce(

@@ -30,8 +30,8 @@ extern "C" {
 #define BG_ABI_VERSION 1
 #define BG_MAX_PEERS 8      /* one NVSwitch domain */
 #define BG_MAX_WORLD 64
-#define BG_LANES 4          /* independent barrier lanes per group (e.g. unshard / grad-reduce / compute / p2p streams) */
-#define BG_MAX_CHANNELS 512 /* max CTAs of a cross-rank kernel (one barrier channel per CTA) */
+#define BG_LANES 6          /* independent barrier lanes per group: unshard / grad-reduce / activations / misc / fused-op push / spare */
+#define BG_MAX_CHANNELS 256 /* max CTAs of a cross-rank kernel (one barrier channel per CTA; the default is one slim CTA per SM) */
 
 typedef struct bg_ctx* bg_ctx_t;
 
@@ -45,7 +45,10 @@ enum bg_err {
 /* ---- library ------------------------------------------------------------------------------------------ */
 int bg_abi_version(void);
 const char* bg_last_error(void);                       /* thread-local message of the last failing call */
-int bg_set_tunable(const char* name, long long value); /* "comm_ctas", "local_ctas", "timeout_ms", "oneshot_bytes" */
+/* "comm_ctas" (CTAs of a cross-rank kernel, default 148 = one 128-thread / <=64-register CTA per SM), "local_ctas", "timeout_ms",
+ * "oneshot_bytes", "nvls_min_bytes" (multicast paths above this size), "nvls_gather" / "nvls_reduce" (0 switches multimem.st /
+ * multimem.ld_reduce off for all-gather / reduce-scatter on multicast-bound buffers) */
+int bg_set_tunable(const char* name, long long value);
 long long bg_get_tunable(const char* name);
 /* how many kernels this library has launched since load (bench.py's gpu_launches) */
 unsigned long long bg_launch_count(void);
@@ -69,7 +72,10 @@ int bg_arena_export_fd(bg_ctx_t ctx, int* fd);                          /* BG_CT
 int bg_arena_import_fd(bg_ctx_t ctx, int peer_rank, int fd);
 int bg_ctx_error_flag(bg_ctx_t ctx, int* flag);                         /* device-side timeout report */
 /* info8[0] = status; [1] = kind (1 signalling a peer, 2 waiting for a peer, 3 fused-GEMM tile reducer);
- * [2] = CTA; [3] = thread or tile; [4] = value last seen; [5], [6] = group index/size or expected count/tiles.
+ * [2] = CTA; [3] = thread or tile; [4] = value last seen; [5], [6] = group index/size or expected count/tiles;
+ * [7] = launch site of a barrier timeout (1 all-gather, 2 reduce-scatter, 3 all-reduce, 6 all-to-all, 7 entry barrier of a fused
+ * GEMM, 8 exit barrier of the all-reduce tile reducer, 10/11 p2p flags, 12 push kernel of the fused all-gather+GEMM), kind 4 = the
+ * gathering GEMM's TMA producer waiting for a block.
  * The reference's analogue is the NCCL watchdog's timeout dump (ProcessGroupNCCL); here a lost peer traps the
  * kernel and leaves this record in mapped host memory. */
 int bg_ctx_error_info(bg_ctx_t ctx, int* info8);
@@ -184,15 +190,39 @@ int bg_gemm_bf16(const void* a, const void* b, void* c, long long m, long long n
 int bg_gemm_reduce_scatter(bg_ctx_t ctx, int gid, int lane, const void* a, const void* b, long long m, long long n, long long k,
                            int layout, const size_t* partial_offs, const size_t* flag_offs, void* out, void* stream);
 
+/* C5/C6 fused with K1: GEMM + ALL-REDUCE (row-parallel forward, layers.py:1110-1114: matmul then reduce_from_tensor_model_parallel
+ * _region; column-parallel dgrad, mappings_group.py:139).  Both shots of the two-shot all-reduce happen inside the fused
+ * operation: partial tiles are scattered to their owners as in bg_gemm_reduce_scatter; the owner's tile reducer sums a tile when
+ * its p partials have landed and immediately broadcasts the rows into EVERY member's out buffer (peer stores, or one multimem.st
+ * when out is multicast-bound); the reducers leave through a cross-rank barrier, so out -- a symmetric bf16 [M][N] buffer,
+ * out_offs -- is complete on every member in stream order.  Deterministic (fixed summation order), fp32 accumulation. */
+int bg_gemm_all_reduce(bg_ctx_t ctx, int gid, int lane, const void* a, const void* b, long long m, long long n, long long k, int layout,
+                       const size_t* partial_offs, const size_t* flag_offs, const size_t* out_offs, void* stream);
+
+/* C7 fused with K1: ALL-GATHER + GEMM (column-parallel forward under Megatron-SP, layers.py:399-417: _all_gather_base into the
+ * global buffer, then matmul; also the row-parallel dgrad, whose dY is gathered, mappings_group.py:243-258).
+ * C[M,N] = gather_M(a_local[M/p,K]) op B.  A slim push kernel on comm_stream (resident beside the GEMM) sends the local rows to
+ * every member's staging buffer (stage_offs: symmetric bf16 [M][K]) in 128-row blocks and counts each block in on the receiver
+ * (flag_offs: symmetric u32[p][M/p/128], zero-initialised); the GEMM's TMA producer reads the rank's own rows from a_local and
+ * every remote block from staging as soon as its counter is complete, walking the blocks in arrival order.  layout 0 (TN) or
+ * 1 (NN); M a multiple of p*128.  C is complete in `stream` order; a_local may be reused after the call in `stream` order. */
+int bg_all_gather_gemm(bg_ctx_t ctx, int gid, int lane, const void* a_local, const size_t* stage_offs, const size_t* flag_offs,
+                       const void* b, void* c, long long m, long long n, long long k, int layout, void* stream, void* comm_stream);
+
 /* ---- NVLS: all-reduce reduced and replicated INSIDE the NVSwitch (multimem.ld_reduce / multimem.st) ---------------------
  * Replaces the tensor-parallel all-reduces (mappings_group.py:19, layers.py:474-480) for large messages, where NCCL itself
  * switches to NVLS: N/p bytes in and N/p out per GPU instead of 2(p-1)/p*N.  One multicast object per group over one
  * symmetric buffer: the group's first rank creates it (-> fd), every other member imports the fd, ALL join (device added),
  * barrier on the host, ALL bind their own arena range (multicast-granularity aligned), then bg_all_reduce_nvls works in
- * place on that buffer and copies the result to dst (dst may be NULL: result left in the buffer).  BG_CTX_VMM contexts only. */
+ * place on that buffer and copies the result to dst (dst may be NULL: result left in the buffer).  BG_CTX_VMM contexts only.
+ * The bound range may be any part of the arena (the host binds the whole region that holds its symmetric buffers): every
+ * collective whose buffer lies inside it at the same offset on all members then uses the switch on its own --
+ * bg_all_reduce (ld_reduce + st), bg_all_gather_cast and the bg_gemm_all_reduce broadcast (multimem.st), bg_reduce_scatter_acc /
+ * _adamw (multimem.ld_reduce) -- above "nvls_min_bytes". */
 int bg_group_mc_create(bg_ctx_t ctx, int gid, size_t bytes, int* fd_out);
 int bg_group_mc_join(bg_ctx_t ctx, int gid, int fd /* -1 on the creator */, size_t bytes);
 int bg_group_mc_bind(bg_ctx_t ctx, int gid, size_t arena_offset);
+int bg_group_mc_disable(bg_ctx_t ctx, int gid);   /* setup failed on some member: the group keeps the peer-to-peer kernels */
 int bg_all_reduce_nvls(bg_ctx_t ctx, int gid, int lane, size_t byte_offset, void* dst, size_t elems, int dtype, float scale,
                        void* stream);
 

@@ -20,7 +20,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_TOOL = "/root/reference/galvatron/tools/checkpoint_convert_h2g.py"
 OUT = os.path.join(ROOT, "tests", "golden", "ckpt_llama_tiny")
-# the TINY spec of hetu-galvatron_b200/smoke_model.py
+# the TINY spec of tests/smoke_model.py
 SPEC = dict(hidden_size=128, intermediate_size=352, num_attention_heads=4, num_key_value_heads=2, num_hidden_layers=2,
             rms_norm_eps=1e-5, vocab_size=512, max_position_embeddings=64, rope_theta=10000.0)
 

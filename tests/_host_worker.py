@@ -65,13 +65,13 @@ def gathered_master_grad(be, u, world, rank):
 
 
 def gather_all_master_grads(model, world, rank):
-    mine = {u.name: (list(u.group.ranks), u.master_grad.detach().float().cpu()) for u in model.model.units}
+    mine = {u.name: (list(u.group.ranks), u.master_grad.detach().float().cpu().clone()) for u in model.model.units}
     allr = [None] * world
     dist.all_gather_object(allr, mine)
     full = {}
     for u in model.model.units:
         if u.dp_type == "ddp" or u.group.size == 1:
-            full[u.name] = u.master_grad.detach().float().cpu()
+            full[u.name] = u.master_grad.detach().float().cpu().clone()
         else:
             full[u.name] = torch.cat([allr[r][u.name][1] for r in u.group.ranks])
     return full
@@ -85,9 +85,11 @@ def main():
     spec = over.pop("_spec", None)
     golden_ckpt, save_to = over.pop("_golden_ckpt", None), over.pop("_save_to", None)
     save_after, n_iters, skip_batches = over.pop("_save_after", 0), over.pop("_iters", 2), over.pop("_skip_batches", 0)
+    clip = over.pop("_clip_grad", None)
     use_cuda = os.environ.get("HOST_TEST_BACKEND", "oracle") == "cuda"
     from oracle import llama_ref
-    from hetu_galvatron_b200 import smoke_model as sm
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import smoke_model as sm
     from hetu_galvatron_b200.core.runtime.backend import get_backend, set_backend
     from hetu_galvatron_b200.core.runtime.utils import get_optimizer_and_param_scheduler
     if use_cuda:   # the product path on real GPUs: NCCL only bootstraps (IPC handle / offset exchange)
@@ -208,6 +210,17 @@ def main():
                     print("DEBUG layer", i, "scale", scale["gpt_dec_%d" % (i + 1)], {k: fit(gl[k], wl[k].grad) for k in gl}, flush=True)
             assert abs(mean_loss - float(ref_loss)) <= 5e-3 * abs(float(ref_loss)), report
             assert report["max_grad_err"] < tol, (report, errs)
+            if clip is not None:
+                # clip_grad_norm (core/runtime/utils.py:124-133): the job-wide L2 norm counts every parameter once -- the oracle's
+                # gradients of the un-parallelised model give the expected value -- and every shard is scaled by the same factor
+                from hetu_galvatron_b200.core.runtime.utils import clip_grad_norm
+                want = float(torch.sqrt(sum(t.grad.float().pow(2).sum() for t in leaves)))
+                got_norm = clip_grad_norm(model, clip)
+                after = gather_all_master_grads(model, world, rank)
+                ratios = [float(after[u.name].norm() / (full_grads[u.name].norm() + 1e-30)) for u in model.model.units]
+                report.update({"clip_norm": got_norm, "clip_norm_oracle": want, "clip_ratios": ratios,
+                               "clip_expected_ratio": min(1.0, clip / (got_norm + 1e-6))})
+                assert abs(got_norm - want) <= 2e-2 * want, report
         else:
             lt = torch.tensor([loss if loss is not None else 0.0, 1.0 if loss is not None else 0.0], dtype=torch.float64, device=dev)
             dist.all_reduce(lt)
@@ -222,13 +235,17 @@ def main():
     if use_cuda:
         report["launches"] = be.launch_count()
         report["fused_gemm_rs_calls"] = getattr(be, "n_fused_gemm_rs", 0)
+        report["fused_calls"] = dict(getattr(be, "n_fused", {}))
     if rank == 0:
         print("HOST_TEST_REPORT " + json.dumps(report), flush=True)
     dist.barrier()
     if use_cuda:
         from hetu_galvatron_b200.core.runtime.backend import reset_backend
+        report["fused_calls"] = dict(getattr(be, "n_fused", {}))
+        report["nvls_groups"] = len(getattr(be, "nvls_regions", {}) or {})
         reset_backend()
     dist.destroy_process_group()
+    return report
 
 
 if __name__ == "__main__":

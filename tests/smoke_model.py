@@ -1,12 +1,17 @@
 """Tiny end-to-end training steps of the Llama family through the public API, checked against the oracle
-(used by ``__graft_entry__.smoke()`` and tests/test_gpu_model.py)."""
+(test infrastructure: used by ``__graft_entry__.smoke()``, tests/_host_worker.py and bench.py's leg parity checks; it lives in
+tests/ so that the product package never imports ``oracle``)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import types
 
 import torch
 
 
 def tiny_args(**over):
-    from .core.runtime.arguments import initialize_galvatron
+    from hetu_galvatron_b200.core.runtime.arguments import initialize_galvatron
     kw = dict(pp_deg=1, global_tp_deg=1, global_cp_deg=1, sdp=0, default_dp_type="zero2", chunks=1, global_train_batch_size=4,
               mixed_precision="bf16", pipeline_type="pipedream_flush", sequence_parallel=False, use_ulysses=False,
               vocab_tp=1, vocab_cp=1, global_checkpoint=0, make_vocab_size_divisible_by=128, init_method_std=0.05, seed=1234,
@@ -19,7 +24,7 @@ TINY = dict(dim=128, ffn_dim=352, n_heads=4, n_kv_heads=2, n_layers=2, norm_eps=
 
 
 def build(args, spec=None):
-    from .llama_hf import config_from_meta, llama_model_hp, set_model_config
+    from hetu_galvatron_b200.llama_hf import config_from_meta, llama_model_hp, set_model_config
     config = set_model_config(config_from_meta(dict(spec or TINY)), args)
     return config, llama_model_hp(config, args)
 
@@ -49,8 +54,8 @@ def oracle_cfg(config, args):
 def run(steps=2, verbose=True, **over):
     """Train the tiny model for ``steps`` iterations on cuda:0 and compare loss + gradients of the first step with the oracle."""
     from oracle import llama_ref
-    from .core.runtime.backend import reset_backend
-    from .core.runtime.utils import get_optimizer_and_param_scheduler
+    from hetu_galvatron_b200.core.runtime.backend import reset_backend
+    from hetu_galvatron_b200.core.runtime.utils import get_optimizer_and_param_scheduler
     reset_backend()
     args = tiny_args(**over)
     torch.manual_seed(args.seed)

@@ -62,7 +62,7 @@ def test_errors_are_return_codes(bg):
     assert L.bg_group_create(None, None, 0, None) == -1
     with pytest.raises(bg.BgError):
         bg.check(L.bg_arena_alloc(None, 16, None))
-    assert bg.get_tunable("comm_ctas") == 296
+    assert bg.get_tunable("comm_ctas") == 148      # one slim CTA per SM
 
 
 def test_c_mirror_of_group_builder_matches_goldens(bg):

@@ -22,6 +22,10 @@ CASES = {
     "tp2_megatron_sp": (2, dict(global_tp_deg=2, vocab_tp=2, sequence_parallel=True)),
     "dp2_zero3": (2, dict(sdp=1, embed_sdp=1)),
     "pp2": (2, dict(pp_deg=2, chunks=2)),
+    # vocabulary rows tp 1 (data parallel over both ranks), layers tp 2: every layer row is wrapped in Module_with_relocation
+    "vtp1_layers_tp2": (2, dict(_strategy_json={"pp_deg": 1, "tp_sizes_enc": "2,2", "tp_consecutive_flags": "1,1", "dp_types_enc": "0,0",
+                                                "use_sp": "0,0", "checkpoint": "0,0", "global_bsz": 4, "chunks": 1,
+                                                "default_dp_type": "zero2", "vtp": 1, "vsp": 0})),
 }
 
 
@@ -33,7 +37,7 @@ def test_load_hf_layered_checkpoint(name):
     assert abs(rep["loss"] - EXPECTED["hf_loss_fp32"]) <= 5e-3 * EXPECTED["hf_loss_fp32"], rep
 
 
-@pytest.mark.parametrize("name", ["tp2", "dp2_zero3"])
+@pytest.mark.parametrize("name", ["tp2", "dp2_zero3", "vtp1_layers_tp2"])
 def test_save_then_load_distributed_checkpoint(name, tmp_path):
     world, over = CASES[name]
     out = str(tmp_path / "ckpt")
@@ -42,9 +46,10 @@ def test_save_then_load_distributed_checkpoint(name, tmp_path):
     assert os.path.isfile(os.path.join(out, "hybrid_parallel_configs.json"))
     it = os.path.join(out, "iter_0")
     assert os.path.isfile(os.path.join(it, "opt_param_scheduler.json"))
-    tp = 2 if name == "tp2" else 1
+    tp = 2 if name in ("tp2", "vtp1_layers_tp2") else 1
     for d in ("model_embed_tokens", "model_layers_0", "model_layers_1", "model_norm", "lm_head"):
-        assert sorted(os.listdir(os.path.join(it, d))) == ["%d.pt" % r for r in range(tp)], d
+        n_files = tp if (name != "vtp1_layers_tp2" or d.startswith("model_layers")) else 1
+        assert sorted(os.listdir(os.path.join(it, d))) == ["%d.pt" % r for r in range(n_files)], d
     assert sorted(os.listdir(os.path.join(it, "optimizer"))) == ["%d.pt" % r for r in range(world)]
     layer = torch.load(os.path.join(it, "model_layers_1", "0.pt"), weights_only=True)
     assert sorted(layer) == ["attention.LayerNorm.weight", "attention.attention.dense.weight",

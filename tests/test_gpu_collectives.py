@@ -25,7 +25,7 @@ def bg():
     import hetu_galvatron_b200._bg as bg
     bg.lib()
     bg.set_tunable("timeout_ms", 20000)
-    bg.set_tunable("comm_ctas", 8)  # 8 virtual ranks x 8 CTAs stay co-resident on one device
+    bg.set_tunable("comm_ctas", 16)  # 8 virtual ranks x 16 slim CTAs stay co-resident on one device
     return bg
 
 
@@ -273,7 +273,7 @@ def test_full_size_round_trip_property(bg, ref):
         for r in range(n):
             assert torch.equal(out[r], masters[r].to(torch.bfloat16).float())
     finally:
-        bg.set_tunable("comm_ctas", 8)
+        bg.set_tunable("comm_ctas", 16)
         w.close()
 
 
