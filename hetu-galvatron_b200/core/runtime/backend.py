@@ -93,10 +93,12 @@ class CudaBackend:
         self.comm = comm
         if os.environ.get("HGB_TIMEOUT_MS"):      # device-side barrier timeout (default 60 s): shorter for debugging runs
             _bg.set_tunable("timeout_ms", int(os.environ["HGB_TIMEOUT_MS"]))
-        self.unshard_stream = torch.cuda.Stream(device=self.device)
-        self.reduce_stream = torch.cuda.Stream(device=self.device)
-        self.p2p_stream = torch.cuda.Stream(device=self.device)
-        self.comm_stream = torch.cuda.Stream(device=self.device)     # push kernels of the fused all-gather + GEMM; overlapped gathers
+        # communication streams are HIGH priority: the CTA distributor then places a slim collective CTA (which fits beside the
+        # persistent GEMM CTAs) ahead of any compute grid that is still waiting for SMs, instead of queueing it behind that grid
+        self.unshard_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self.reduce_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self.p2p_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)  # push kernels of the fused all-gather + GEMM; overlapped gathers
         self.fuse_gemm_rs = os.environ.get("HGB_FUSE_GEMM_RS", "1") != "0"
         self.fuse_gemm_ar = os.environ.get("HGB_FUSE_GEMM_AR", "1") != "0"
         self.fuse_ag_gemm = os.environ.get("HGB_FUSE_AG_GEMM", "1") != "0"

@@ -886,6 +886,7 @@ extern "C" int bg_all_gather_gemm(bg_ctx_t c, int gid, int lane, const void* a_l
     }
     BG_CUDA(cudaEventRecord(ev_in, st));                 // a_local is produced by the work already in `stream`
     BG_CUDA(cudaStreamWaitEvent(cs, ev_in, 0));
+    s.site = 12;
     AgSignal sg = {};
     for (int i = 0; i < p; ++i) sg.flag[i] = (uint32_t*)flags.p[i];
     sg.chunk_vecs = (size_t)128 * k * 2 / 16;

@@ -42,7 +42,10 @@ class World:
         self.comms = bg.BgComm.local_world(n, device=0, arena_bytes=arena)
         self.group = CommGroup(list(range(n)))
         self.streams = [torch.cuda.Stream() for _ in range(n)]
-        self.comm_streams = [torch.cuda.Stream() for _ in range(n)]
+        # communication streams are HIGH priority (as in the backend): the CTA distributor serves a high-priority grid before a
+        # low-priority one that is waiting for an SM (here: another virtual rank's 128-CTA GEMM), so a push kernel is never
+        # stuck behind a GEMM that cannot be placed yet
+        self.comm_streams = [torch.cuda.Stream(priority=-1) for _ in range(n)]
 
     def sym(self, nbytes):
         bufs = [c.sym_alloc(self.group, nbytes) for c in self.comms]

@@ -57,17 +57,30 @@ def test_smoke_entry():
     ge.smoke()
 
 
-@pytest.mark.parametrize("n", [2, 4, 8])
-def test_fused_gemm_reduce_scatter(n):
-    """GEMM whose epilogue reduce-scatters over the TP group (partial tiles -> owner's HBM -> tile reducer) vs
-    cuBLAS + NCCL reduce_scatter, at the Llama-3-8B row-parallel shapes; needs n real GPUs."""
-    _need(n)
+def _torchrun(n, script, port, env=None, timeout=600):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
-                          "127.0.0.1", "--master-port", str(29800 + n), os.path.join(root, "scripts", "test_fused_gemm_rs.py")],
-                         capture_output=True, text=True, timeout=600)
+    return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
+                           "127.0.0.1", "--master-port", str(port), os.path.join(root, "scripts", script)],
+                          capture_output=True, text=True, timeout=timeout, env=dict(os.environ, **(env or {})))
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_fused_gemm_collectives(n):
+    """GEMM + reduce-scatter, GEMM + all-reduce and all-gather + GEMM on n real GPUs at the Llama-3-8B tensor-parallel shapes vs
+    cuBLAS + NCCL (reductions) / the plain tcgen05 GEMM on the gathered operand (bit-exact)."""
+    _need(n)
+    out = _torchrun(n, "test_fused_collectives.py", 29800 + n)
     assert out.returncode == 0 and "FUSED_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_collectives_vs_nccl(n):
+    """The slim peer-to-peer kernels and their multicast (NVLS) variants on n real GPUs: bit-exact data movement, reductions
+    within bf16 of NCCL."""
+    _need(n)
+    out = _torchrun(n, "bench_collectives.py", 29850 + n, env={"BENCH_QUICK": "1"})
+    assert out.returncode == 0 and "COLLECTIVES_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
 @pytest.mark.parametrize("world,name", [(1, "tp1"), (2, "tp2"), (2, "dp2_zero3")])
@@ -86,16 +99,3 @@ def test_checkpoint_load_save_resume(world, name, tmp_path):
     assert abs(a["losses"][0] - EXPECTED["hf_loss_fp32"]) <= 5e-3 * EXPECTED["hf_loss_fp32"]
     b = launch(world, dict(over, load=out, distributed_checkpoint=True, load_iteration=2, _skip_batches=2, _iters=1), backend="cuda")
     assert abs(b["losses"][0] - a["losses"][2]) <= 1e-6 * abs(a["losses"][2]), (a["losses"], b["losses"], json.dumps(over))
-
-
-@pytest.mark.parametrize("n", [2, 8])
-def test_nvls_all_reduce(n):
-    """Opt-in VMM arena + in-switch (multimem) all-reduce against NCCL; a box without NVSwitch multicast must still run the
-    ordinary peer kernels on the VMM arena (NVLS_UNSUPPORTED)."""
-    _need(n)
-    import subprocess
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
-                          "127.0.0.1", "--master-port", str(29850 + n), os.path.join(root, "scripts", "test_nvls.py")],
-                         capture_output=True, text=True, timeout=600, env=dict(os.environ, NVLS_MAX_MB="256"))
-    assert out.returncode == 0 and ("NVLS_OK" in out.stdout or "NVLS_UNSUPPORTED" in out.stdout), out.stdout[-3000:] + out.stderr[-3000:]
