@@ -160,7 +160,10 @@ def build_model(opts, strategy, backend=None):
                                 use_ulysses=False, init_method_std=0.02, seed=1234, local_rank=1, lr=1e-4, adam_weight_decay=0.01,
                                 make_vocab_size_divisible_by=128, vocab_tp=strategy.get("vtp", 1), model_size=opts.model,
                                 default_dp_type=strategy.get("default_dp_type", "zero2"), chunks=strategy["chunks"],
-                                global_train_batch_size=strategy["global_bsz"], pp_deg=strategy["pp_deg"])
+                                global_train_batch_size=strategy["global_bsz"], pp_deg=strategy["pp_deg"],
+                                # (this runtime's key, next to the Search Engine's: the memory profile the strategy was searched with
+                                # assumed the SwiGLU / RMSNorm outputs are recomputed in backward instead of saved)
+                                recompute_activations=bool(strategy.get("recompute_activations", 0)))
     args.vocab_size = spec["vocab_size"]
     config = set_model_config(config_from_meta(spec), args)
     model = llama_model_hp(config, args)

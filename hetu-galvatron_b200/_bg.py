@@ -74,6 +74,9 @@ SIGNATURES = {
     "bg_cast": (_i, [_vp, _i, _vp, _i, _sz, _f, _i, _vp]),
     "bg_rmsnorm_fwd": (_i, [_vp, _vp, _vp, _vp, _ll, _ll, _f, _vp]),
     "bg_rmsnorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _ll, _i, _vp]),
+    "bg_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _ll, _f, _vp]),
+    "bg_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _ll, _i, _vp]),
+    "bg_bias_gelu": (_i, [_vp, _vp, _vp, _vp, _ll, _ll, _i, _vp]),
     "bg_swiglu_fwd": (_i, [_vp, _vp, _ll, _ll, _vp]),
     "bg_swiglu_bwd": (_i, [_vp, _vp, _vp, _ll, _ll, _vp]),
     "bg_qkv_rope": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _ll, _ll, _ll, _ll, _i, _vp]),

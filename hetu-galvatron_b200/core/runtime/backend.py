@@ -561,6 +561,40 @@ class CudaBackend:
         self.bg.check(L.bg_rmsnorm_bwd(_p(dy2), _p(x2), _p(weight), _p(rstd), _p(dx), _p(dwp), x2.shape[0], x2.shape[1], npart, _s()))
         return dx.view_as(x), dwp.sum(0).to(weight.dtype)
 
+    def layernorm_fwd(self, x, weight, bias, eps):
+        """LayerNorm with bias (GPT / BERT families): -> (y, mean[rows], rstd[rows]) fp32 statistics."""
+        x2 = x.reshape(-1, x.shape[-1])
+        y = torch.empty_like(x2)
+        mean = torch.empty(x2.shape[0], dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        self.bg.check(self.bg.lib().bg_layernorm_fwd(_p(x2), _p(weight), _p(bias), _p(y), _p(mean), _p(rstd), x2.shape[0], x2.shape[1],
+                                                     float(eps), _s()))
+        return y.view_as(x), mean, rstd
+
+    def layernorm_bwd(self, dy, x, weight, mean, rstd):
+        x2, dy2 = x.reshape(-1, x.shape[-1]), dy.reshape(-1, x.shape[-1])
+        dx = torch.empty_like(x2)
+        npart = min(296, max(1, x2.shape[0]))
+        dwp = torch.empty(npart, x2.shape[1], dtype=torch.float32, device=x.device)
+        dbp = torch.empty_like(dwp)
+        self.bg.check(self.bg.lib().bg_layernorm_bwd(_p(dy2), _p(x2), _p(weight), _p(mean), _p(rstd), _p(dx), _p(dwp), _p(dbp),
+                                                     x2.shape[0], x2.shape[1], npart, _s()))
+        return dx.view_as(x), dwp.sum(0).to(weight.dtype), dbp.sum(0).to(weight.dtype)
+
+    def bias_gelu_fwd(self, x, bias, tanh_form=True):
+        x2 = x.reshape(-1, x.shape[-1])
+        y = torch.empty_like(x2)
+        self.bg.check(self.bg.lib().bg_bias_gelu(_p(x2), _p(bias) if bias is not None else None, None, _p(y), x2.shape[0], x2.shape[1],
+                                                 1 if tanh_form else 0, _s()))
+        return y.view_as(x)
+
+    def bias_gelu_bwd(self, dy, x, bias, tanh_form=True):
+        x2, dy2 = x.reshape(-1, x.shape[-1]), dy.reshape(-1, x.shape[-1])
+        dx = torch.empty_like(x2)
+        self.bg.check(self.bg.lib().bg_bias_gelu(_p(x2), _p(bias) if bias is not None else None, _p(dy2), _p(dx), x2.shape[0], x2.shape[1],
+                                                 1 if tanh_form else 0, _s()))
+        return dx.view_as(x)
+
     def swiglu_fwd(self, gate_up):
         rows, two_f = gate_up.reshape(-1, gate_up.shape[-1]).shape
         y = torch.empty(gate_up.shape[:-1] + (two_f // 2,), dtype=gate_up.dtype, device=gate_up.device)
@@ -604,15 +638,25 @@ class CudaBackend:
         # the reference casts cos/sin to the activation dtype before applying them (apply_rotary_pos_emb)
         return torch.cos(freqs).to(dtype).float().contiguous(), torch.sin(freqs).to(dtype).float().contiguous()
 
-    def attention(self, q, k, v, causal, softmax_scale):
+    def attention(self, q, k, v, causal, softmax_scale, key_mask=None):
         """Attention is a LIBRARY call, as in the reference (transformer.py:495 calls flash-attn; K3 is not a collective and
         is outside the hot-path scope).  On B200 the fastest library in the image is cuDNN's fused SDPA (tcgen05 kernels:
         measured 1459 TFLOP/s fwd vs 370 for flash-attn 2's sm80-class kernels, profiles/r01_attention_libraries.jsonl), reached
         through torch SDPA; HGB_ATTN=flash selects flash-attn 2.  q [b,s,n,d], k/v [b,s,ng,d] (GQA un-expanded).  Differentiable."""
-        if self.attn_impl != "cudnn":
-            return None
         import torch.nn.functional as F
         from torch.nn.attention import SDPBackend, sdpa_kernel
+        if key_mask is not None:
+            # BERT's padding mask (bert_hf/BertModel_sequential.py: get_extended_attention_mask): key j of sample b is visible iff
+            # key_mask[b, j]; fused SDPA with an additive mask (cuDNN where it accepts the mask, the memory-efficient kernel else)
+            assert not causal
+            bias = torch.zeros(key_mask.shape[0], 1, 1, key_mask.shape[1], dtype=q.dtype, device=q.device)
+            bias.masked_fill_(~key_mask.bool()[:, None, None, :], float("-inf"))
+            with sdpa_kernel([SDPBackend.CUDNN_ATTENTION, SDPBackend.EFFICIENT_ATTENTION, SDPBackend.MATH]):
+                o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), attn_mask=bias,
+                                                   scale=softmax_scale, enable_gqa=k.shape[2] != q.shape[2])
+            return o.transpose(1, 2)
+        if self.attn_impl != "cudnn":
+            return None
         with sdpa_kernel([SDPBackend.CUDNN_ATTENTION]):
             o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=causal,
                                                scale=softmax_scale, enable_gqa=k.shape[2] != q.shape[2])

@@ -203,6 +203,7 @@ class ShardedUnit:
         self._started = set()          # params whose G slice holds this step's gradient
         self._w_valid = self.w_pool is None
         self._unshard_event = None
+        self._reduce_event = None      # the last reduction of this unit (reduce stream) has read G
         self._reduced_this_step = False
         self._pending = False          # backward ran since the last reduction
         self.n_unshard = self.n_reduce = 0
@@ -390,6 +391,9 @@ class ShardedUnit:
         self._started.clear()
         self._pending = False
         self.n_reduce += 1
+        # the reduction reads G on the reduce stream: the NEXT backward of this layer (another microbatch under
+        # --no_async_grad_reduce) must not overwrite G before it has been read -- _pre_backward waits for this event
+        self._reduce_event = be.reduce_done_event()
         self.release_grads()
 
     def finish_step(self):
@@ -513,6 +517,9 @@ class DataParallelModule(nn.Module):
 
     def _pre_backward(self):
         unit = self.unit
+        if unit._reduce_event is not None:      # G is about to be rewritten: its previous reduction must have read it
+            unit.be.wait_event(unit._reduce_event)
+            unit._reduce_event = None
         unit.unshard()
         if self.prev_unit is not None:
             self.prev_unit.unshard(prefetch=True)   # backward prefetch: the previous layer's re-gather overlaps this backward

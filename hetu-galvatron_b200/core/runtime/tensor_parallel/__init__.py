@@ -8,7 +8,7 @@ from .mappings_group import (copy_to_tensor_model_parallel_region_group, gather_
                              get_tensor_model_parallel_world_size_group, reduce_from_tensor_model_parallel_region_group,
                              reduce_scatter_to_sequence_parallel_region_group, scatter_to_sequence_parallel_region_group,
                              scatter_to_tensor_model_parallel_region_group)
-from .transformer import AttnMaskType, AttnType, ParallelAttention, ParallelMLP, RMSNorm
+from .transformer import AttnMaskType, AttnType, LayerNorm, ParallelAttention, ParallelMLP, RMSNorm
 
 
 def colummn_row_reset_parameters(self):

@@ -52,7 +52,13 @@ def _write_wgrad(weight, dy2d, x2d):
     if sink is None:
         return be.gemm(dy2d, x2d, "nt")
     unit = weight._bg_unit
-    be.gemm(dy2d, x2d, "nt", out=sink, accumulate=unit.grad_started(weight))
+    if sink.dtype == dy2d.dtype:
+        be.gemm(dy2d, x2d, "nt", out=sink, accumulate=unit.grad_started(weight))
+    else:
+        # --reduce_in_fp32: the unsharded gradient buffer is fp32 (arguments.py:187); the tcgen05 GEMM writes bf16, so the wgrad
+        # goes through a bf16 tile buffer and the cast kernel accumulates it into the fp32 buffer
+        tmp = be.gemm(dy2d, x2d, "nt")
+        be.cast(tmp, sink, accumulate=unit.grad_started(weight))
     unit.mark_grad(weight)
     return None
 

@@ -120,8 +120,11 @@ class _UlyssesFn(torch.autograd.Function):
 
 class _FlashAttnFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, causal, softmax_scale):
-        out, lse, rng = get_backend().attention_fwd(q, k, v, causal, softmax_scale)
+    def forward(ctx, q, k, v, causal, softmax_scale, key_mask=None):
+        if key_mask is None:
+            out, lse, rng = get_backend().attention_fwd(q, k, v, causal, softmax_scale)
+        else:
+            out, lse, rng = get_backend().attention_fwd(q, k, v, causal, softmax_scale, key_mask)
         ctx.save_for_backward(q, k, v, out, lse)
         ctx.causal, ctx.scale, ctx.rng = causal, softmax_scale, rng
         return out
@@ -130,7 +133,64 @@ class _FlashAttnFn(torch.autograd.Function):
     def backward(ctx, dout):
         q, k, v, out, lse = ctx.saved_tensors
         dq, dk, dv = get_backend().attention_bwd(dout, q, k, v, out, lse, ctx.causal, ctx.scale, ctx.rng)
-        return dq, dk, dv, None, None
+        return dq, dk, dv, None, None, None
+
+
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        y, mean, rstd = get_backend().layernorm_fwd(x.contiguous(), weight, bias, eps)
+        ctx.save_for_backward(x, weight, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, rstd = ctx.saved_tensors
+        dx, dw, db = get_backend().layernorm_bwd(dy.contiguous(), x.contiguous(), weight, mean, rstd)
+        return dx, dw, db, None
+
+
+class LayerNorm(nn.Module):
+    """``torch.nn.LayerNorm`` of the GPT / BERT families (gpt_hf/GPTModel_tensor_parallel.py:34, bert_hf/BertModel_tensor_parallel.py)
+    as one fused row kernel forward and one backward: y = (x - mean) * rstd * weight + bias, fp32 math, one rounding."""
+
+    def __init__(self, hidden_size, eps=1e-5, params_dtype=torch.float32, device=None, sequence_parallel=False):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.empty(hidden_size, dtype=params_dtype, device=device))
+        self.bias = nn.Parameter(torch.empty(hidden_size, dtype=params_dtype, device=device))
+        self._sequence_parallel = bool(sequence_parallel)
+        if self.weight.device.type != "meta":
+            self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.ones_(self.weight)
+        nn.init.zeros_(self.bias)
+        # under Megatron-SP the norm sees only the local sequence slice: its grads are summed over the TP group on the last
+        # microbatch (sp_grad_reduce.py:104-123); (re)tag here, materialising from meta makes new Parameter objects
+        setattr(self.weight, "sequence_parallel", self._sequence_parallel)
+        setattr(self.bias, "sequence_parallel", self._sequence_parallel)
+
+    def forward(self, x):
+        return _LayerNormFn.apply(x, self.weight, self.bias, self.eps)
+
+
+class _BiasGeluFn(torch.autograd.Function):
+    """gelu(x + bias) of the GPT / BERT MLP in one pass (transformer.py:150-160 ``bias_gelu_impl``); dbias = column sums of dx."""
+
+    @staticmethod
+    def forward(ctx, x, bias, tanh_form):
+        x = x.contiguous()
+        ctx.save_for_backward(x, bias)
+        ctx.tanh_form = tanh_form
+        return get_backend().bias_gelu_fwd(x, bias, tanh_form)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, bias = ctx.saved_tensors
+        dx = get_backend().bias_gelu_bwd(dy.contiguous(), x, bias, ctx.tanh_form)
+        db = None if bias is None else dx.reshape(-1, dx.shape[-1]).float().sum(0).to(bias.dtype)
+        return dx, db, None
 
 
 class _CpGatherKvFn(torch.autograd.Function):
@@ -181,38 +241,50 @@ def _recompute_activations():
         return False
 
 
-def _attention(q, k, v, causal, scale):
+def _attention(q, k, v, causal, scale, key_mask=None):
     be = get_backend()
     fn = getattr(be, "attention", None)
-    out = fn(q, k, v, causal, scale) if fn is not None else None   # differentiable library call (cuDNN SDPA on B200)
-    return out if out is not None else _FlashAttnFn.apply(q, k, v, causal, scale)
+    if fn is None:
+        out = None
+    elif key_mask is None:
+        out = fn(q, k, v, causal, scale)                            # differentiable library call (cuDNN SDPA on B200)
+    else:
+        out = fn(q, k, v, causal, scale, key_mask)
+    return out if out is not None else _FlashAttnFn.apply(q, k, v, causal, scale, key_mask)
 
 
 # ---------------------------------------------------------------------------------------------------------------
 # layer modules
 # ---------------------------------------------------------------------------------------------------------------
 class ParallelMLP(nn.Module):
-    """h -> 2*ffn (gate|up, column-parallel) -> swiglu -> h (row-parallel) (transformer.py:82-166)."""
+    """h -> 4h (column-parallel) -> activation -> h (row-parallel) (transformer.py:82-166).
+    Llama: gated (gate|up, swiglu), no biases.  GPT / BERT (``add_bias_linear``, not gated): bias + GeLU in one fused pass
+    (``bias_gelu_impl``, :150-160), the output bias is returned for the caller to add (``skip_bias_add``, :162-166)."""
 
     def __init__(self, config, is_expert=False, tp_group=None, params_dtype=torch.float32, device=None):
         super().__init__()
         self.tp_group = tp_group
         ffn = config.ffn_hidden_size
         self.gated = getattr(config, "gated_linear_unit", True)
-        self.dense_h_to_4h = ColumnParallelLinear(config.hidden_size, ffn * 2 if self.gated else ffn, config=config, bias=False,
-                                                  gather_output=False, tp_group=tp_group, params_dtype=params_dtype, device=device)
-        self.dense_4h_to_h = RowParallelLinear(ffn, config.hidden_size, config=config, bias=False, input_is_parallel=True,
-                                               tp_group=tp_group, params_dtype=params_dtype, device=device)
+        self.add_bias = bool(getattr(config, "add_bias_linear", False))
+        self.gelu_tanh = bool(getattr(config, "gelu_tanh", True))
+        self.dense_h_to_4h = ColumnParallelLinear(config.hidden_size, ffn * 2 if self.gated else ffn, config=config, bias=self.add_bias,
+                                                  gather_output=False, skip_bias_add=True, tp_group=tp_group,
+                                                  params_dtype=params_dtype, device=device)
+        self.dense_4h_to_h = RowParallelLinear(ffn, config.hidden_size, config=config, bias=self.add_bias, input_is_parallel=True,
+                                               skip_bias_add=True, tp_group=tp_group, params_dtype=params_dtype, device=device)
 
     def forward(self, hidden_states, input_recipe=None):
-        gate_up, _ = self.dense_h_to_4h(hidden_states, recompute=input_recipe)
+        gate_up, bias = self.dense_h_to_4h(hidden_states, recompute=input_recipe)
         if self.gated:
+            if bias is not None:
+                gate_up = gate_up + bias
             inter = _SwigluFn.apply(gate_up)
             # --recompute_activations: the 4h->h GEMM keeps gate_up (which SwiGLU's own backward holds anyway) instead of the
             # SwiGLU output and redoes the elementwise pass in backward
             recipe = ("swiglu", gate_up) if _recompute_activations() else None
             return self.dense_4h_to_h(inter, recompute=recipe)
-        inter = torch.nn.functional.gelu(gate_up)
+        inter = _BiasGeluFn.apply(gate_up, bias, self.gelu_tanh)
         return self.dense_4h_to_h(inter)
 
 
@@ -242,34 +314,47 @@ class ParallelAttention(nn.Module):
             assert n_heads % sp_group.size == 0, "num_attention_heads must be divisible by the Ulysses degree"  # :642
         self.np_local, self.ng_local = n_heads // world, n_groups // world
         self.r = self.np_local // self.ng_local
+        add_bias = bool(getattr(config, "add_bias_linear", False))       # GPT / BERT: biases on both projections (:600-640)
         self.query_key_value = ColumnParallelLinear(config.hidden_size, (n_heads + 2 * n_groups) * self.hn, config=config,
-                                                    bias=False, gather_output=False, tp_group=tp_group,
+                                                    bias=add_bias, gather_output=False, tp_group=tp_group,
                                                     params_dtype=params_dtype, device=device)
-        self.dense = RowParallelLinear(n_heads * self.hn, config.hidden_size, config=config, bias=False,
+        self.dense = RowParallelLinear(n_heads * self.hn, config.hidden_size, config=config, bias=add_bias, skip_bias_add=True,
                                        input_is_parallel=True, tp_group=tp_group, params_dtype=params_dtype, device=device)
         self.softmax_scale = 1.0 / math.sqrt(self.hn)
+        self._identity_rope = {}
+
+    def _no_rope(self, seq, device):
+        """Families with learned absolute positions (GPT, BERT) run the same split + relayout kernel with cos = 1, sin = 0."""
+        key = (seq, str(device))
+        if key not in self._identity_rope:
+            self._identity_rope[key] = (torch.ones(seq, self.hn // 2, dtype=torch.float32, device=device),
+                                        torch.zeros(seq, self.hn // 2, dtype=torch.float32, device=device))
+        return self._identity_rope[key]
 
     def forward(self, hidden_states, attention_mask=None, encoder_output=None, inference_params=None, rotary_pos_emb=None,
                 input_recipe=None):
         # hidden_states [sq, b, h]; rotary_pos_emb = (cos, sin) fp32 tables [sq_local, hn/2] for this rank's positions
         mixed, _ = self.query_key_value(hidden_states, recompute=input_recipe)   # [s, b, ng*(r+2)*hn]
-        cos, sin = rotary_pos_emb
+        cos, sin = rotary_pos_emb if rotary_pos_emb is not None else self._no_rope(mixed.shape[0], mixed.device)
         stage_group = self.sp_group if self.use_ulysses else None
         q, k, v = _QkvRopeFn.apply(mixed, cos, sin, self.ng_local, self.r, self.hn, stage_group)
         causal = self.attn_mask_type == AttnMaskType.causal
+        # padding mask (BERT): [b, s] bool over the keys, True = attend (the reference builds the extended [b,1,1,s] additive
+        # mask in bert_hf/BertModel_sequential.py and hands it to every layer)
+        key_mask = attention_mask if (not causal and attention_mask is not None) else None
         if self.use_ulysses:
             p = self.sp_group.size
             if self.ng_local % p:  # too few KV heads to scatter: expand as the reference does (:842-848)
                 rep = self.np_local // self.ng_local
                 k, v = k.repeat_interleave(rep, dim=2), v.repeat_interleave(rep, dim=2)
             q, k, v = _UlyssesFn.apply(self.sp_group, True, q, k, v)       # [b, s, n/p, hn]
-            ctxt = _attention(q, k, v, causal, self.softmax_scale)
+            ctxt = _attention(q, k, v, causal, self.softmax_scale, key_mask)
             (ctxt,) = _UlyssesFn.apply(self.sp_group, False, ctxt)         # [b, s/p, n, hn]
         elif self.use_cp:
             assert causal, "context parallelism is implemented for causal self-attention"
             ctxt = _cp_attention(q, k, v, self.cp_group, self.softmax_scale)   # [b, s/c, np, hn]
         else:
-            ctxt = _attention(q, k, v, causal, self.softmax_scale)          # [b, s, np, hn]
+            ctxt = _attention(q, k, v, causal, self.softmax_scale, key_mask)  # [b, s, np, hn]
         b, s = ctxt.shape[0], ctxt.shape[1]
         ctxt = ctxt.reshape(b, s, -1).transpose(0, 1).contiguous()          # "b s h d -> s b (h d)"
         return self.dense(ctxt)

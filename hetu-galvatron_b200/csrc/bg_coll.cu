@@ -85,7 +85,7 @@ template <> struct Cvt<float, float> {
 struct AgSignal {
     uint32_t* flag[BG_MAX_PEERS];   // receiver q's counters: [source member][chunk]
     size_t chunk_vecs;
-    int n_chunks;
+    int n_chunks, split;            // a chunk is complete when `split` units have been counted in
 };
 
 template <typename SrcT, typename DstT, bool kSignal>
@@ -94,23 +94,20 @@ __global__ void BG_SLIM all_gather_push_kernel(const __grid_constant__ PeerPtrs 
     using C = Cvt<SrcT, DstT>;
     sync_peers<false, false, true>(s);  // every member has finished consuming its dst (it reached this kernel)
     const size_t nvec = shard_elems / C::kElems;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t dst_base = (size_t)s.me * shard_elems * sizeof(DstT);
-    const size_t cv = kSignal ? sg.chunk_vecs : nvec;
-    int ci = 0;
-    for (size_t c0 = 0; c0 < nvec; c0 += cv, ++ci) {
-        const size_t c1 = c0 + cv < nvec ? c0 + cv : nvec;
-        for (size_t v0 = c0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < c1; v0 += stride * kUnroll) {
+    if (!kSignal) {
+        const size_t stride = (size_t)gridDim.x * blockDim.x;
+        for (size_t v0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += stride * kUnroll) {
             uint4 regs[kUnroll][C::kRegs];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
                 size_t v = v0 + u * stride;
-                if (v < c1) C::load(src, v * C::kElems, regs[u]);
+                if (v < nvec) C::load(src, v * C::kElems, regs[u]);
             }
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
                 size_t v = v0 + u * stride;
-                if (v < c1) {
+                if (v < nvec) {
                     uint4 o = C::convert(regs[u]);
                     if (dst_mc != nullptr) {
                         mm_st_16(dst_mc + dst_base + v * 16, o);       // replicated by the switch
@@ -123,15 +120,41 @@ __global__ void BG_SLIM all_gather_push_kernel(const __grid_constant__ PeerPtrs 
                 }
             }
         }
-        if (kSignal) {
-            __threadfence_system();
-            __syncthreads();
-            const int t = threadIdx.x;
-            if (t < s.n && t != s.me)
-                asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(sg.flag[t] + (size_t)s.me * sg.n_chunks + ci) : "memory");
-        }
+        sync_peers<true, true, false>(s);  // my stores are visible everywhere; everyone's shard has landed here
+        return;
     }
-    if (!kSignal) sync_peers<true, true, false>(s);  // my stores are visible everywhere; everyone's shard has landed here
+    // kSignal: a chunk (one 128-row block of the GEMM) is cut into `split` units; a unit is pushed by ONE CTA, which then makes its
+    // stores visible (one .sys fence per unit, not per chunk and grid) and counts the unit in on every receiver.  Units are dealt
+    // out in chunk order, so block c of every slot is complete before block c+1.
+    const size_t unit_vecs = sg.chunk_vecs / sg.split;
+    const int n_units = sg.n_chunks * sg.split;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const size_t u0 = (size_t)unit * unit_vecs, u1 = u0 + unit_vecs;
+        for (size_t v0 = u0 + threadIdx.x; v0 < u1; v0 += (size_t)blockDim.x * kUnroll) {
+            uint4 regs[kUnroll][C::kRegs];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                size_t v = v0 + (size_t)u * blockDim.x;
+                if (v < u1) C::load(src, v * C::kElems, regs[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                size_t v = v0 + (size_t)u * blockDim.x;
+                if (v < u1) {
+                    uint4 o = C::convert(regs[u]);
+                    for (int k = 0; k < s.n; ++k) {
+                        int p = s.me + k; if (p >= s.n) p -= s.n;
+                        st16(dst.p[p] + dst_base + v * 16, o);
+                    }
+                }
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        const int t = threadIdx.x;
+        if (t < s.n && t != s.me)
+            asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(sg.flag[t] + (size_t)s.me * sg.n_chunks + unit / sg.split) : "memory");
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -211,16 +234,23 @@ __device__ __forceinline__ void rs_epilogue(const RsOut& o, size_t v, float* acc
     }
 }
 
-// PMAX = 2, 4 or 8 >= group size: V = kInFlight / PMAX vectors of PMAX peer loads each are in flight per thread.
-// kMc: the source is multicast-bound -- ONE multimem.ld_reduce per vector returns the members' sum (fp32 accumulation in the
-// switch, rounded to the source dtype), kInFlight vectors in flight.
+// PMAX = 2, 4 or 8 >= group size: V = 8 / PMAX vectors x PMAX loads (the rank's own copy + the peers in ring order) are in flight
+// per thread.  (Keeping only peer loads in flight and reading the own copy one vector ahead was measured SLOWER at p = 2: the
+// serialised local loads, 7 x ~700 cycles, outlast the peer latency.)  kMc: the source is multicast-bound -- ONE
+// multimem.ld_reduce per vector returns the members' sum (fp32 accumulation in the switch, rounded to the source dtype).
+template <int PMAX, int kEpi>
+struct RsPlan {
+    // (the AdamW epilogue keeps 12 more registers of optimizer state live: half the vectors in flight below 8 peers)
+    static constexpr int V = (kEpi == kEpiAdamW && PMAX < 8 ? kInFlight / 2 : kInFlight) / PMAX;
+    static constexpr int V_MC = kEpi == kEpiAdamW ? 4 : 8;
+};
+
 template <int PMAX, bool kSrcBf16, int kEpi, bool kMc>
 __global__ void BG_SLIM reduce_scatter_pull_kernel(const __grid_constant__ PeerPtrs src, const char* __restrict__ src_mc, const __grid_constant__ RsOut o,
                                                    size_t shard_elems, float prescale, float postscale, const __grid_constant__ Sig s) {
     constexpr int E = kSrcBf16 ? 8 : 4;  // elements per 16-B source vector
     constexpr int NL = kMc ? 1 : PMAX;
-    // (the AdamW epilogue keeps 12 more registers of optimizer state live: fewer vectors in flight below 8 peers)
-    constexpr int V = (kEpi == kEpiAdamW && NL < 8 ? kInFlight / 2 : kInFlight) / NL;
+    constexpr int V = kMc ? RsPlan<PMAX, kEpi>::V_MC : RsPlan<PMAX, kEpi>::V;
     sync_peers<false, false, true>(s);  // every member's src is complete (its producer kernels finished before this one)
     const size_t nvec = shard_elems / E;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -235,10 +265,11 @@ __global__ void BG_SLIM reduce_scatter_pull_kernel(const __grid_constant__ PeerP
                 if (v < nvec) in[u][0] = kSrcBf16 ? mm_ld_reduce_bf16(src_mc + slice_off + v * 16) : mm_ld_reduce_f32(src_mc + slice_off + v * 16);
             } else {
 #pragma unroll
-                for (int p = 0; p < NL; ++p) {
-                    if (p < s.n && v < nvec) {
-                        const char* a = src.p[p] + slice_off + v * 16;
-                        in[u][p] = (p == s.me) ? ld16_stream(a) : ld16_peer(a);
+                for (int k = 0; k < NL; ++k) {
+                    if (k < s.n && v < nvec) {
+                        int q = s.me + k; if (q >= s.n) q -= s.n;       // own copy, then ring order: every source serves one reader at a time
+                        const char* a = src.p[q] + slice_off + v * 16;
+                        in[u][k] = k == 0 ? ld16_stream(a) : ld16_peer(a);
                     }
                 }
             }
@@ -250,15 +281,11 @@ __global__ void BG_SLIM reduce_scatter_pull_kernel(const __grid_constant__ PeerP
             float acc[E];
 #pragma unroll
             for (int i = 0; i < E; ++i) acc[i] = 0.f;
-            // fixed summation order (group order 0..n-1): run-to-run deterministic.  Each rank's contribution is
-            // scaled by `prescale` before the sum, as the reference pre-divides (_runtime_utils.py:852).
-            if (kMc) {
-                rs_accumulate<kSrcBf16>(in[u][0], acc, prescale);
-            } else {
+            // fixed summation order (own slice, then the peers in ring order): run-to-run deterministic.  Each rank's contribution
+            // is scaled by `prescale` before the sum, as the reference pre-divides (_runtime_utils.py:852).
 #pragma unroll
-                for (int p = 0; p < NL; ++p)
-                    if (p < s.n) rs_accumulate<kSrcBf16>(in[u][p], acc, prescale);
-            }
+            for (int k = 0; k < NL; ++k)
+                if (kMc || k < s.n) rs_accumulate<kSrcBf16>(in[u][k], acc, prescale);
             rs_epilogue<E, kEpi>(o, v, acc, postscale);
         }
     }
@@ -461,33 +488,47 @@ struct A2AArgs {
     int n_tensors;
 };
 
+// element i of a (batch, rows, row_vec) block -> vector offsets in the source (peer q's buffer) and in my destination
+struct A2AIdx { long long src, dst; };
+__device__ __forceinline__ A2AIdx a2a_index(const A2ADev& d, unsigned i, int me, int q) {
+    const unsigned row_vec = (unsigned)d.row_vec, rows = (unsigned)d.rows;
+    const unsigned c = i % row_vec, r = i / row_vec;
+    const unsigned row = r % rows, b = r / rows;
+    A2AIdx x;
+    x.src = (long long)b * d.src_bs + (long long)row * d.src_rs + (long long)me * d.src_me_off + c;
+    x.dst = (long long)b * d.dst_bs + (long long)row * d.dst_rs + (long long)q * d.dst_peer_off + c;
+    return x;
+}
+
+// One source at a time (ring order: rank r reads from r+1, r+2, ...: every source serves ONE reader at a time), 8 peer loads in
+// flight per thread; the block the rank keeps for itself is a plain local copy.  Indices are recomputed for the store instead of
+// being kept in registers across the loads.
 __global__ void BG_SLIM all_to_all_rows_kernel(const __grid_constant__ A2AArgs a, const __grid_constant__ Sig s) {
     sync_peers<false, false, true>(s);
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    constexpr int U = kInFlight;
+    const unsigned stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
     for (int ti = 0; ti < a.n_tensors; ++ti) {
         const A2ADev& d = a.t[ti];
-        const long long per_peer = d.batch * d.rows * d.row_vec;
-        for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < (size_t)d.total_vec; i0 += stride * kUnroll) {
-            uint4 regs[kUnroll];
-            long long dsts[kUnroll];
+        const unsigned per_peer = (unsigned)(d.batch * d.rows * d.row_vec);
+        for (int k = 0; k < s.n; ++k) {
+            int q = s.me + k; if (q >= s.n) q -= s.n;
+            const char* sp = d.src.p[q];
+            for (unsigned i0 = t0; i0 < per_peer; i0 += stride * U) {
+                uint4 regs[U];
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                size_t i = i0 + u * stride;
-                dsts[u] = -1;
-                if (i < (size_t)d.total_vec) {
-                    int k = (int)(i / per_peer);
-                    long long r = (long long)(i - (size_t)k * per_peer);
-                    int q = s.me + k; if (q >= s.n) q -= s.n;
-                    long long c = r % d.row_vec; r /= d.row_vec;
-                    long long row = r % d.rows, b = r / d.rows;
-                    const char* sp = d.src.p[q] + (b * d.src_bs + row * d.src_rs + (long long)s.me * d.src_me_off + c) * 16;
-                    regs[u] = (q == s.me) ? ld16_stream(sp) : ld16_peer(sp);
-                    dsts[u] = b * d.dst_bs + row * d.dst_rs + (long long)q * d.dst_peer_off + c;
+                for (int u = 0; u < U; ++u) {
+                    const unsigned i = i0 + u * stride;
+                    if (i < per_peer) {
+                        const char* ad = sp + a2a_index(d, i, s.me, q).src * 16;
+                        regs[u] = k == 0 ? ld16_stream(ad) : ld16_peer(ad);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const unsigned i = i0 + u * stride;
+                    if (i < per_peer) st16(d.dst + a2a_index(d, i, s.me, q).dst * 16, regs[u]);
                 }
             }
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u)
-                if (dsts[u] >= 0) st16(d.dst + dsts[u] * 16, regs[u]);
         }
     }
     sync_peers<true, false, false>(s);
@@ -622,7 +663,9 @@ static int launch_reduce_scatter(bg_ctx_t c, int gid, int lane, const size_t* sr
     BG_CUDA(cudaSetDevice(c->device));
     const char* mc = g_tun.nvls_reduce ? mc_ptr(c, gid, *g, src_offs, shard_elems * g->n * ssz) : nullptr;
     if (mc && shard_elems * ssz < (size_t)g_tun.nvls_min_bytes) mc = nullptr;
-    const int in_flight_vecs = (epi == kEpiAdamW && (mc || g->n <= 4) ? kInFlight / 2 : kInFlight) / (mc ? 1 : g->n <= 2 ? 2 : g->n <= 4 ? 4 : 8);
+    const bool adam = epi == kEpiAdamW;
+    const int pmax = g->n <= 2 ? 2 : g->n <= 4 ? 4 : 8;
+    const int in_flight_vecs = mc ? (adam ? 4 : 8) : (adam && pmax < 8 ? kInFlight / 2 : kInFlight) / pmax;
     int grid = comm_grid(shard_elems / per / in_flight_vecs + 1, kThreads, g->n);
     cudaStream_t st = (cudaStream_t)stream;
     const bool bf = src_dtype == BG_BF16;
@@ -740,11 +783,12 @@ extern "C" int bg_all_to_all_rows(bg_ctx_t c, int gid, int lane, const bg_a2a_de
         a.t[i].src_bs = d.src_bs / per; a.t[i].src_rs = d.src_rs / per; a.t[i].src_me_off = d.src_me_off / per;
         a.t[i].dst_bs = d.dst_bs / per; a.t[i].dst_rs = d.dst_rs / per; a.t[i].dst_peer_off = d.dst_peer_off / per;
         a.t[i].total_vec = d.batch * d.rows * a.t[i].row_vec * g->n;
-        if ((size_t)a.t[i].total_vec > max_vec) max_vec = (size_t)a.t[i].total_vec;
+        if (d.batch * d.rows * a.t[i].row_vec >= (1ll << 32)) return fail(BG_EINVAL, "all_to_all: more than 2^32 16-B vectors per peer");
+        if ((size_t)(a.t[i].total_vec / g->n) > max_vec) max_vec = (size_t)(a.t[i].total_vec / g->n);
     }
     s.site = 6;
     BG_CUDA(cudaSetDevice(c->device));
-    int grid = comm_grid(max_vec / kUnroll + 1, kThreads, g->n);
+    int grid = comm_grid(max_vec / kInFlight + 1, kThreads, g->n);
     all_to_all_rows_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a, s);
     BG_CHECK_LAUNCH();
     return BG_OK;
@@ -891,9 +935,12 @@ extern "C" int bg_all_gather_gemm(bg_ctx_t c, int gid, int lane, const void* a_l
     for (int i = 0; i < p; ++i) sg.flag[i] = (uint32_t*)flags.p[i];
     sg.chunk_vecs = (size_t)128 * k * 2 / 16;
     sg.n_chunks = n_chunks;
-    // grid: fixed by the shape (the consumer waits for exactly this many arrivals per chunk)
+    // a chunk is cut into `split` units (each pushed and counted in by one CTA) so that all CTAs of the push kernel are busy
+    // from the first chunk on: the largest power of two with n_chunks * split <= comm_ctas, at least 8 rows per unit
+    sg.split = 1;
+    while (sg.split < 16 && (long long)n_chunks * sg.split * 2 <= g_tun.comm_ctas) sg.split *= 2;
     const size_t shard_elems = (size_t)rows_local * k;
-    int grid = comm_grid(sg.chunk_vecs / kUnroll + 1, kThreads, p);
+    int grid = (int)((long long)n_chunks * sg.split < g_tun.comm_ctas ? (long long)n_chunks * sg.split : g_tun.comm_ctas);
     {
         PeerPtrs dst = stage;
         all_gather_push_kernel<__nv_bfloat16, __nv_bfloat16, true><<<grid, kThreads, 0, cs>>>(dst, nullptr, (const __nv_bfloat16*)a_local,
@@ -901,7 +948,7 @@ extern "C" int bg_all_gather_gemm(bg_ctx_t c, int gid, int lane, const void* a_l
         BG_CHECK_LAUNCH();
     }
     BG_CUDA(cudaEventRecord(ev_out, cs));
-    rc = bg_gemm_gather_launch(a_local, stage.p[g->me], b, out, m, n, k, layout, p, g->me, (const uint32_t*)flags.p[g->me], (uint32_t)grid,
+    rc = bg_gemm_gather_launch(a_local, stage.p[g->me], b, out, m, n, k, layout, p, g->me, (const uint32_t*)flags.p[g->me], (uint32_t)sg.split,
                                (unsigned long long)g_tun.timeout_ms * 1000000ull, c->err_dev, st);
     if (rc) return rc;
     BG_CUDA(cudaMemsetAsync(flags.p[g->me], 0, (size_t)p * n_chunks * sizeof(uint32_t), st));   // peers count again only after the next entry barrier

@@ -176,6 +176,172 @@ __global__ void __launch_bounds__(kThreads) rmsnorm_bwd_kernel(const uint4* __re
 }
 
 // ---------------------------------------------------------------------------------------------
+// LayerNorm with bias (GPT / BERT families: torch.nn.LayerNorm in gpt_hf/GPTModel_tensor_parallel.py:34,56 and
+// bert_hf/BertModel_tensor_parallel.py): fp32 math, y = (x - mean) * rstd * w + b, one rounding.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) layernorm_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w,
+                                                                 const uint4* __restrict__ b, uint4* __restrict__ y,
+                                                                 float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                                 long long rows, int nvec, float eps) {
+    __shared__ float smem[32];
+    const float inv_n = 1.f / (float)(nvec * 8);
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const uint4* xr = x + r * nvec;
+        uint4 xv[kMaxVpt];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxVpt; ++j) {
+            int v = threadIdx.x + j * kThreads;
+            if (v < nvec) {
+                xv[j] = ld16_stream(xr + v);
+                float f[8];
+                unpack8(xv[j], f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s += f[i];
+            }
+        }
+        const float mean = block_reduce<false>(s, smem) * inv_n;
+        float ss = 0.f;               // two-pass variance on the register-resident row (no cancellation)
+#pragma unroll
+        for (int j = 0; j < kMaxVpt; ++j) {
+            int v = threadIdx.x + j * kThreads;
+            if (v < nvec) {
+                float f[8];
+                unpack8(xv[j], f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ss += (f[i] - mean) * (f[i] - mean);
+            }
+        }
+        const float rstd = rsqrtf(block_reduce<false>(ss, smem) * inv_n + eps);
+        if (threadIdx.x == 0) { mean_out[r] = mean; rstd_out[r] = rstd; }
+#pragma unroll
+        for (int j = 0; j < kMaxVpt; ++j) {
+            int v = threadIdx.x + j * kThreads;
+            if (v < nvec) {
+                float f[8], g[8], c[8];
+                unpack8(xv[j], f);
+                unpack8(__ldg(w + v), g);
+                unpack8(__ldg(b + v), c);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = (f[i] - mean) * rstd * g[i] + c[i];
+                st16(y + r * nvec + v, pack8(f));
+            }
+        }
+    }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) with g = dy * w;  dw_partial[cta] = sum dy * xhat, db_partial[cta] = sum dy
+__global__ void __launch_bounds__(kThreads) layernorm_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
+                                                                 const uint4* __restrict__ w, const float* __restrict__ mean_in,
+                                                                 const float* __restrict__ rstd_in, uint4* __restrict__ dx,
+                                                                 float* __restrict__ dw_partial, float* __restrict__ db_partial,
+                                                                 long long rows, int nvec) {
+    __shared__ float smem[32];
+    // one 16-B vector per thread per pass keeps the accumulators in registers for rows up to kThreads * 8 * kMaxVpt columns
+    float dw[kMaxVpt][8], db[kMaxVpt][8];
+#pragma unroll
+    for (int j = 0; j < kMaxVpt; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { dw[j][i] = 0.f; db[j][i] = 0.f; }
+    const float inv_n = 1.f / (float)(nvec * 8);
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const float mean = mean_in[r], rstd = rstd_in[r];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxVpt; ++j) {
+            int v = threadIdx.x + j * kThreads;
+            if (v < nvec) {
+                float xh[8], g[8], wv[8];
+                unpack8(ld16_stream(x + r * nvec + v), xh);
+                unpack8(ld16_stream(dy + r * nvec + v), g);
+                unpack8(__ldg(w + v), wv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    xh[i] = (xh[i] - mean) * rstd;
+                    dw[j][i] += g[i] * xh[i];
+                    db[j][i] += g[i];
+                    const float gw = g[i] * wv[i];
+                    s1 += gw;
+                    s2 += gw * xh[i];
+                }
+            }
+        }
+        s1 = block_reduce<false>(s1, smem) * inv_n;
+        s2 = block_reduce<false>(s2, smem) * inv_n;
+#pragma unroll
+        for (int j = 0; j < kMaxVpt; ++j) {
+            int v = threadIdx.x + j * kThreads;
+            if (v < nvec) {       // re-read (L2-resident) instead of holding xhat and g*w for the whole row in registers
+                float xh[8], g[8], wv[8], o[8];
+                unpack8(ld16_stream(x + r * nvec + v), xh);
+                unpack8(ld16_stream(dy + r * nvec + v), g);
+                unpack8(__ldg(w + v), wv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = rstd * (g[i] * wv[i] - s1 - (xh[i] - mean) * rstd * s2);
+                st16(dx + r * nvec + v, pack8(o));
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxVpt; ++j) {
+        int v = threadIdx.x + j * kThreads;
+        if (v < nvec) {
+            float4* d = reinterpret_cast<float4*>(dw_partial + ((size_t)blockIdx.x * nvec + v) * 8);
+            d[0] = make_float4(dw[j][0], dw[j][1], dw[j][2], dw[j][3]);
+            d[1] = make_float4(dw[j][4], dw[j][5], dw[j][6], dw[j][7]);
+            float4* e = reinterpret_cast<float4*>(db_partial + ((size_t)blockIdx.x * nvec + v) * 8);
+            e[0] = make_float4(db[j][0], db[j][1], db[j][2], db[j][3]);
+            e[1] = make_float4(db[j][4], db[j][5], db[j][6], db[j][7]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bias + GeLU (tanh form, Megatron's bias_gelu_impl: transformer.py:150-160 with bias_gelu_fusion; HF "gelu_new"), and the
+// exact erf form (HF BERT "gelu"):  y = gelu(x + b);  backward: dx = dy * gelu'(x + b)   (dbias = column sums of dx)
+// ---------------------------------------------------------------------------------------------
+template <bool kTanh>
+__device__ __forceinline__ float gelu_f(float v) {
+    if (kTanh) return v * 0.5f * (1.f + tanhf(0.79788456f * v * (1.f + 0.044715f * v * v)));
+    return v * 0.5f * (1.f + erff(v * 0.70710678f));
+}
+template <bool kTanh>
+__device__ __forceinline__ float gelu_grad_f(float v) {
+    if (kTanh) {
+        const float t = tanhf(0.79788456f * v * (1.f + 0.044715f * v * v));
+        return 0.5f * v * ((1.f - t * t) * (0.79788456f + 0.1070322243f * v * v)) + 0.5f * (1.f + t);
+    }
+    return 0.5f * (1.f + erff(v * 0.70710678f)) + v * 0.3989422804f * __expf(-0.5f * v * v);
+}
+
+template <bool kTanh, bool kBackward>
+__global__ void __launch_bounds__(kThreads) bias_gelu_kernel(const uint4* __restrict__ x, const uint4* __restrict__ bias,
+                                                             const uint4* __restrict__ dy, uint4* __restrict__ out,
+                                                             long long rows, int cvec) {
+    const size_t total = (size_t)rows * cvec, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const size_t c = i % cvec;
+        float f[8], b[8];
+        unpack8(ld16_stream(x + i), f);
+        if (bias != nullptr) {
+            unpack8(__ldg(bias + c), b);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] += b[k];
+        }
+        if (kBackward) {
+            float d[8];
+            unpack8(ld16_stream(dy + i), d);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = d[k] * gelu_grad_f<kTanh>(f[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = gelu_f<kTanh>(f[k]);
+        }
+        st16(out + i, pack8(f));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // swiglu: gate_up = [rows, 2*ffn] (gate = first half, up = second; transformer.py:122-124)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) swiglu_fwd_kernel(const uint4* __restrict__ gu, uint4* __restrict__ y,
@@ -480,11 +646,52 @@ extern "C" int bg_ce_bwd(void* logits, int dtype, const long long* target, const
     return BG_OK;
 }
 
+extern "C" int bg_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, long long rows,
+                                long long cols, float eps, void* stream) {
+    if (cols % 8 || cols > (long long)kThreads * 8 * kMaxVpt) return fail(BG_EINVAL, "layernorm: cols %lld must be a multiple of 8 and <= %d", cols, kThreads * 8 * kMaxVpt);
+    if (rows <= 0) return BG_OK;
+    const int grid = (int)(rows < g_tun.local_ctas ? rows : g_tun.local_ctas);
+    layernorm_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)w, (const uint4*)b, (uint4*)y, mean, rstd,
+                                                                      rows, (int)(cols / 8), eps);
+    BG_CHECK_LAUNCH();
+    return BG_OK;
+}
+
+extern "C" int bg_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
+                                float* dw_partial, float* db_partial, long long rows, long long cols, int n_partial, void* stream) {
+    if (cols % 8 || cols > (long long)kThreads * 8 * kMaxVpt) return fail(BG_EINVAL, "layernorm: cols %lld must be a multiple of 8 and <= %d", cols, kThreads * 8 * kMaxVpt);
+    if (n_partial < 1) return fail(BG_EINVAL, "layernorm_bwd: n_partial must be >= 1");
+    layernorm_bwd_kernel<<<n_partial, kThreads, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint4*)x, (const uint4*)w, mean, rstd, (uint4*)dx,
+                                                                           dw_partial, db_partial, rows, (int)(cols / 8));
+    BG_CHECK_LAUNCH();
+    return BG_OK;
+}
+
+extern "C" int bg_bias_gelu(const void* x, const void* bias, const void* dy, void* out, long long rows, long long cols, int tanh_form,
+                            void* stream) {
+    if (cols % 8) return fail(BG_EINVAL, "bias_gelu: cols %lld must be a multiple of 8", cols);
+    if (rows <= 0) return BG_OK;
+    const int grid = local_grid((size_t)rows * cols / 8, kThreads);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint4 *xv = (const uint4*)x, *bv = (const uint4*)bias, *dv = (const uint4*)dy;
+    if (dy == nullptr) {
+        if (tanh_form) bias_gelu_kernel<true, false><<<grid, kThreads, 0, st>>>(xv, bv, dv, (uint4*)out, rows, (int)(cols / 8));
+        else bias_gelu_kernel<false, false><<<grid, kThreads, 0, st>>>(xv, bv, dv, (uint4*)out, rows, (int)(cols / 8));
+    } else {
+        if (tanh_form) bias_gelu_kernel<true, true><<<grid, kThreads, 0, st>>>(xv, bv, dv, (uint4*)out, rows, (int)(cols / 8));
+        else bias_gelu_kernel<false, true><<<grid, kThreads, 0, st>>>(xv, bv, dv, (uint4*)out, rows, (int)(cols / 8));
+    }
+    BG_CHECK_LAUNCH();
+    return BG_OK;
+}
+
 // loads every kernel of this file up front (see bg_preload_coll in bg_coll.cu)
 int bg_preload_ops() {
 #define K(f) reinterpret_cast<const void*>(&f)
     const void* kernels[] = {K((cast_kernel<true, true>)), K((cast_kernel<true, false>)), K((cast_kernel<false, true>)), K((cast_kernel<false, false>)),
-                             K(rmsnorm_fwd_kernel), K(rmsnorm_bwd_kernel), K(swiglu_fwd_kernel), K(swiglu_bwd_kernel), K(qkv_rope_kernel),
+                             K(rmsnorm_fwd_kernel), K(rmsnorm_bwd_kernel), K(layernorm_fwd_kernel), K(layernorm_bwd_kernel),
+                             K((bias_gelu_kernel<true, false>)), K((bias_gelu_kernel<false, false>)), K((bias_gelu_kernel<true, true>)),
+                             K((bias_gelu_kernel<false, true>)), K(swiglu_fwd_kernel), K(swiglu_bwd_kernel), K(qkv_rope_kernel),
                              K(ce_rowmax_kernel<true>), K(ce_rowmax_kernel<false>), K(ce_sumexp_kernel<true>), K(ce_sumexp_kernel<false>),
                              K(ce_bwd_kernel<true>), K(ce_bwd_kernel<false>)};
 #undef K

@@ -157,6 +157,15 @@ int bg_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, long long
                    void* stream);
 int bg_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, float* dw_partial,
                    long long rows, long long cols, int n_partial, void* stream);
+/* LayerNorm with bias (GPT / BERT families: gpt_hf/GPTModel_tensor_parallel.py:34,56; fp32 math, one rounding).  backward:
+ * dw_partial / db_partial are [n_partial][cols] fp32 per-CTA partial sums (the caller adds them up). */
+int bg_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, long long rows, long long cols,
+                     float eps, void* stream);
+int bg_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx, float* dw_partial,
+                     float* db_partial, long long rows, long long cols, int n_partial, void* stream);
+/* bias + GeLU of the GPT / BERT MLP (transformer.py:150-160 bias_gelu_impl): out = gelu(x + bias) when dy == NULL, else
+ * out = dy * gelu'(x + bias).  tanh_form 1 = Megatron's fused / HF gelu_new, 0 = exact erf.  bias may be NULL. */
+int bg_bias_gelu(const void* x, const void* bias, const void* dy, void* out, long long rows, long long cols, int tanh_form, void* stream);
 int bg_swiglu_fwd(const void* gate_up, void* y, long long rows, long long ffn, void* stream);
 int bg_swiglu_bwd(const void* dy, const void* gate_up, void* dgate_up, long long rows, long long ffn, void* stream);
 /* fused QKV split + RoPE + [s,b,ng,(r+2)*hn] -> q [b,s,ng*r,hn], k/v [b,s,ng,hn] relayout; backward=1 is the exact

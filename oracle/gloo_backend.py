@@ -236,6 +236,35 @@ class OracleBackend:
         dw = (g * xh).reshape(-1, x.shape[-1]).sum(0)
         return dx.to(x.dtype), dw.to(weight.dtype)
 
+    def layernorm_fwd(self, x, weight, bias, eps):
+        xf = x.float()
+        mean = xf.mean(-1, keepdim=True)
+        rstd = torch.rsqrt((xf - mean).pow(2).mean(-1, keepdim=True) + eps)
+        return ((xf - mean) * rstd * weight.float() + bias.float()).to(x.dtype), mean.reshape(-1), rstd.reshape(-1)
+
+    def layernorm_bwd(self, dy, x, weight, mean, rstd):
+        xf, g = x.float(), dy.float()
+        m, r = mean.view(*x.shape[:-1], 1), rstd.view(*x.shape[:-1], 1)
+        xh = (xf - m) * r
+        gw = g * weight.float()
+        dx = r * (gw - gw.mean(-1, keepdim=True) - xh * (gw * xh).mean(-1, keepdim=True))
+        return dx.to(x.dtype), (g * xh).reshape(-1, x.shape[-1]).sum(0).to(weight.dtype), g.reshape(-1, x.shape[-1]).sum(0).to(weight.dtype)
+
+    @staticmethod
+    def _gelu(v, tanh_form):
+        return F.gelu(v, approximate="tanh" if tanh_form else "none")
+
+    def bias_gelu_fwd(self, x, bias, tanh_form=True):
+        v = x.float() if bias is None else x.float() + bias.float()
+        return self._gelu(v, tanh_form).to(x.dtype)
+
+    def bias_gelu_bwd(self, dy, x, bias, tanh_form=True):
+        v = (x.float() if bias is None else x.float() + bias.float()).detach().requires_grad_(True)
+        with torch.enable_grad():
+            y = self._gelu(v, tanh_form)
+        (dv,) = torch.autograd.grad(y, v, dy.float())
+        return dv.to(x.dtype)
+
     def swiglu_fwd(self, gate_up):
         g, u = torch.chunk(gate_up.float(), 2, dim=-1)
         return (F.silu(g) * u).to(gate_up.dtype)
@@ -284,11 +313,13 @@ class OracleBackend:
         p = torch.softmax(scores.masked_fill(mask, float("-inf")), -1)
         return (p @ vf).transpose(1, 2).contiguous().to(q.dtype)
 
-    def attention_fwd(self, q, k, v, causal, softmax_scale):
+    def attention_fwd(self, q, k, v, causal, softmax_scale, key_mask=None):
         rep = q.shape[2] // k.shape[2]
         qf, kf, vf = q.float(), k.float().repeat_interleave(rep, 2), v.float().repeat_interleave(rep, 2)
         qf, kf, vf = [t.transpose(1, 2) for t in (qf, kf, vf)]                          # [b, n, s, d]
         scores = qf @ kf.transpose(-1, -2) * softmax_scale
+        if key_mask is not None:      # padding mask: key j of sample b is visible iff key_mask[b, j]
+            scores = scores.masked_fill(~key_mask.bool()[:, None, None, :], float("-inf"))
         if causal:
             s = scores.shape[-1]
             scores = scores.masked_fill(torch.triu(torch.ones(s, s, dtype=torch.bool), 1), float("-inf"))

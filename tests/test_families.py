@@ -1,0 +1,55 @@
+"""The GPT and BERT families (galvatron/models/gpt_hf, bert_hf) on the product's core: N ranks over gloo run the family's layers /
+schedules on the oracle backend and must reproduce the single-process oracle (oracle/gpt_bert_ref.py, pinned to HF GPT-2 / BERT)
+on the global batch -- loss 5e-3 rel, per-parameter gradients 3e-2 rel-L2.  Strategy shapes follow BASELINE.json configs 1, 3, 4."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_PORT = [29300]
+
+
+def launch(world, config, timeout=600, backend="oracle"):
+    _PORT[0] += 1
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(_PORT[0] + os.getpid() % 500), HOST_TEST_CONFIG=json.dumps(config), OMP_NUM_THREADS="1" if world >= 4 else "2",
+                   HOST_TEST_BACKEND=backend)
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_family_worker.py")], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=timeout)[0] for p in procs]
+    for rank, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, "rank %d failed:\n%s" % (rank, out[-4000:])
+    line = [l for l in outs[0].splitlines() if l.startswith("HOST_TEST_REPORT ")][-1]
+    return json.loads(line[len("HOST_TEST_REPORT "):])
+
+
+CASES = {
+    # BASELINE config 1: GPT pure data parallel on one rank (the plumbing case) -- and its BERT twin
+    "gpt_world1": (1, dict(_family="gpt")),
+    "bert_world1": (1, dict(_family="bert")),
+    "gpt_world1_ckpt_chunks2": (1, dict(_family="gpt", global_checkpoint=1, chunks=2)),
+    "gpt_tp2": (2, dict(_family="gpt", global_tp_deg=2, vocab_tp=2)),
+    "gpt_tp2_megatron_sp": (2, dict(_family="gpt", global_tp_deg=2, vocab_tp=2, sequence_parallel=True)),
+    "gpt_dp2_zero3": (2, dict(_family="gpt", sdp=1, embed_sdp=1)),
+    "bert_tp2": (2, dict(_family="bert", global_tp_deg=2, vocab_tp=2)),
+    "bert_tp2_megatron_sp": (2, dict(_family="bert", global_tp_deg=2, vocab_tp=2, sequence_parallel=True)),
+    "bert_ulysses2": (2, dict(_family="bert", global_tp_deg=2, use_ulysses=True, sequence_parallel=True, vocab_tp=2)),
+    # BASELINE config 3 shape: GPT PP2 x TP2 (Megatron-SP) x ZeRO-2, 1F1B-flush
+    "gpt_baseline3_pp2_tp2_sp_zero2": (4, dict(_family="gpt", pp_deg=2, global_tp_deg=2, vocab_tp=2, sequence_parallel=True, default_dp_type="zero2",
+                                               chunks=4, pipeline_type="pipedream_flush", global_train_batch_size=8)),
+    # BASELINE config 4 shape: BERT Ulysses-SP x DP (grads reduce over DP x SP)
+    "bert_baseline4_ulysses2_dp2": (4, dict(_family="bert", global_tp_deg=2, use_ulysses=True, sequence_parallel=True, vocab_tp=2,
+                                            default_dp_type="zero2", chunks=2, global_train_batch_size=8)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_family(name):
+    world, cfg = CASES[name]
+    rep = launch(world, dict(cfg))
+    assert rep["max_grad_err"] < 3e-2 and rep["loss_step1"] < rep["loss"]

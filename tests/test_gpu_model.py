@@ -99,3 +99,37 @@ def test_checkpoint_load_save_resume(world, name, tmp_path):
     assert abs(a["losses"][0] - EXPECTED["hf_loss_fp32"]) <= 5e-3 * EXPECTED["hf_loss_fp32"]
     b = launch(world, dict(over, load=out, distributed_checkpoint=True, load_iteration=2, _skip_batches=2, _iters=1), backend="cuda")
     assert abs(b["losses"][0] - a["losses"][2]) <= 1e-6 * abs(a["losses"][2]), (a["losses"], b["losses"], json.dumps(over))
+
+
+# ---- GPT / BERT families on the product path (LayerNorm, bias + GeLU, learned positions, padding-mask attention) ----------------------
+def _family_cases():
+    from test_families import CASES
+    return CASES
+
+
+@pytest.mark.parametrize("name", ["gpt_world1", "bert_world1", "gpt_world1_ckpt_chunks2"])
+def test_families_one_gpu(name):
+    _need(1)
+    from test_families import launch as launch_family
+    world, cfg = _family_cases()[name]
+    rep = launch_family(world, dict(cfg), backend="cuda")
+    assert rep["max_grad_err"] < 3e-2 and rep["launches"] > 0
+
+
+@pytest.mark.parametrize("name", ["gpt_tp2", "gpt_tp2_megatron_sp", "gpt_dp2_zero3", "bert_tp2", "bert_tp2_megatron_sp", "bert_ulysses2"])
+def test_families_two_gpus(name):
+    _need(2)
+    from test_families import launch as launch_family
+    world, cfg = _family_cases()[name]
+    rep = launch_family(world, dict(cfg), backend="cuda")
+    assert rep["max_grad_err"] < 3e-2 and rep["launches"] > 0
+
+
+@pytest.mark.parametrize("name", ["gpt_baseline3_pp2_tp2_sp_zero2", "bert_baseline4_ulysses2_dp2"])
+def test_families_four_gpus(name):
+    """BASELINE.json configs 3 and 4 at the tiny model's size: GPT PP2 x TP2 x ZeRO-2 1F1B, BERT Ulysses x DP."""
+    _need(4)
+    from test_families import launch as launch_family
+    world, cfg = _family_cases()[name]
+    rep = launch_family(world, dict(cfg), backend="cuda")
+    assert rep["max_grad_err"] < 3e-2 and rep["launches"] > 0
