@@ -244,15 +244,25 @@ def reduction_checksum(model, step_fn, world):
 
 
 def summarize_comm(prof, steps):
-    """{kind: calls/step, ms/step, achieved bus GB/s (nccl-tests convention), fraction of 900 nominal / 770 measured}"""
+    """{kind: calls/step, ms/step, achieved bus GB/s (nccl-tests convention), fraction of 900 nominal / 770 measured}.  Times are
+    CUDA-event spans of each call ON ITS STREAM, launch to completion: they include waiting for the slowest peer to arrive and the
+    SM sharing with whatever compute runs beside the collective (side-stream collectives are hidden behind the GEMMs on purpose), so
+    these are in-step figures, below the stand-alone rates of profiles/r02_collectives_*gpu.jsonl.  A fused GEMM + collective is
+    judged against its own roofline: the slower of FLOPs / measured GEMM peak and NVLink bytes / 770 GB/s."""
+    peak, _ = measured_peaks()
     out = {}
     for kind, recs in sorted(prof.items()):
-        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in recs)
-        nbytes = sum(b for _, _, b in recs)
+        ms = sum(r[0].elapsed_time(r[1]) for r in recs)
+        nbytes = sum(r[2] for r in recs)
+        flops = sum(r[3] for r in recs) if len(recs[0]) > 3 else 0.0
         gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         out[kind] = {"calls_per_step": round(len(recs) / steps, 1), "ms_per_step": round(ms / steps, 3), "bus_bytes_per_step": int(nbytes / steps),
                      "bus_GBps": round(gbs, 1), "frac_of_900_nominal": round(gbs / NVLINK_NOMINAL_GBS, 3),
                      "frac_of_770_measured": round(gbs / NVLINK_MEASURED_GBS, 3)}
+        if flops > 0 and ms > 0:
+            bound_ms = sum(max(r[3] / (peak * 1e12), r[2] / (NVLINK_MEASURED_GBS * 1e9)) for r in recs) * 1e3
+            out[kind].update({"tflops": round(flops / (ms * 1e-3) / 1e12, 1), "roofline_ms_per_step": round(bound_ms / steps, 3),
+                              "frac_of_fused_roofline": round(bound_ms / ms, 3)})
     return out
 
 

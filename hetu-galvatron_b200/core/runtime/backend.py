@@ -116,10 +116,11 @@ class CudaBackend:
             self.comm = None
 
     # ---- in-step timing of the collectives (bench.py path legs) ----------------------------------------------------
-    def _timed(self, kind, bus_bytes, stream=None):
+    def _timed(self, kind, bus_bytes, stream=None, flops=0.0):
         """Context manager: when ``comm_profile`` is a dict, bracket the launch with CUDA events on its stream and record the
-        algorithmic bus bytes (nccl-tests convention: AG/RS/A2A (p-1)/p*N, AR 2(p-1)/p*N, p2p N) of the call."""
-        return _Timed(self, kind, bus_bytes, stream)
+        algorithmic bus bytes (nccl-tests convention: AG/RS/A2A (p-1)/p*N, AR 2(p-1)/p*N, p2p N) of the call -- and, for a fused
+        GEMM + collective, the GEMM's FLOPs (its roofline is the slower of FLOPs / GEMM peak and bytes / NVLink)."""
+        return _Timed(self, kind, bus_bytes, stream, flops)
 
     # ---- memory -------------------------------------------------------------------------------------------
     def sym_alloc(self, group, nbytes):
@@ -497,7 +498,7 @@ class CudaBackend:
         code, m_, n_, k_ = self._mnk(a, b, layout)
         buf = self.staging(group, m_ * n_ * 2)
         r = buf.data_bytes
-        with self._timed("gemm_all_reduce", 2.0 * (group.size - 1) / group.size * m_ * n_ * 2):
+        with self._timed("gemm_all_reduce", 2.0 * (group.size - 1) / group.size * m_ * n_ * 2, flops=2.0 * m_ * n_ * k_):
             self.comm.gemm_all_reduce(group, a, b, m_, n_, k_, code, buf, r, 3 * r, 2 * r)
         self.n_fused["gemm_ar"] += 1
         # the symmetric result buffer is rewritten by the next fused all-reduce of this group: hand out a private copy
@@ -520,7 +521,7 @@ class CudaBackend:
         n_ = b.shape[0] if code == 0 else b.shape[1]
         buf = self.staging(group, m_ * k_ * 2)
         out = torch.empty(m_, n_, dtype=torch.bfloat16, device=a_local.device)
-        with self._timed("all_gather_gemm", (p - 1) / p * m_ * k_ * 2):
+        with self._timed("all_gather_gemm", (p - 1) / p * m_ * k_ * 2, flops=2.0 * m_ * n_ * k_):
             self.comm.all_gather_gemm(group, a_local, b, out, m_, n_, k_, code, buf, 0, 3 * buf.data_bytes + self.FLAG_BYTES // 2,
                                       self.comm_stream)
         a_local.record_stream(self.comm_stream)
@@ -538,7 +539,7 @@ class CudaBackend:
         n_ = b.shape[0] if code == 0 else b.shape[1]
         buf = self.staging(group, m_ * n_ * 2)
         out = torch.empty(m_ // group.size, n_, dtype=torch.bfloat16, device=a.device)
-        with self._timed("gemm_reduce_scatter", (group.size - 1) / group.size * m_ * n_ * 2):
+        with self._timed("gemm_reduce_scatter", (group.size - 1) / group.size * m_ * n_ * 2, flops=2.0 * m_ * n_ * k_):
             self.comm.gemm_reduce_scatter(group, a, b, m_, n_, k_, code, buf, buf.data_bytes, 3 * buf.data_bytes, out)
         self.n_fused_gemm_rs = getattr(self, "n_fused_gemm_rs", 0) + 1
         self.n_fused["gemm_rs"] += 1
@@ -712,8 +713,8 @@ class CudaBackend:
 
 
 class _Timed:
-    def __init__(self, be, kind, bus_bytes, stream):
-        self.be, self.kind, self.bus_bytes, self.stream = be, kind, bus_bytes, stream
+    def __init__(self, be, kind, bus_bytes, stream, flops=0.0):
+        self.be, self.kind, self.bus_bytes, self.stream, self.flops = be, kind, bus_bytes, stream, flops
 
     def __enter__(self):
         prof = self.be.comm_profile
@@ -726,7 +727,7 @@ class _Timed:
         prof = self.be.comm_profile
         if prof is not None and exc[0] is None:
             self.e1.record(self.stream or torch.cuda.current_stream())
-            prof.setdefault(self.kind, []).append((self.e0, self.e1, float(self.bus_bytes)))
+            prof.setdefault(self.kind, []).append((self.e0, self.e1, float(self.bus_bytes), float(self.flops)))
         return False
 
 

@@ -1,1 +1,40 @@
-"""Import shim (test infrastructure only): flash_attn.ops.rms_norm imports this extension."""
+"""Stand-in (test infrastructure only) for flash-attn's compiled ``dropout_layer_norm`` extension, which this image lacks:
+``flash_attn.ops.rms_norm.RMSNorm`` -- the norm of the reference's Llama family (llama_hf/LlamaModel_tensor_parallel.py:2,48) --
+calls it.  Restates, in plain torch, the two entry points for the configuration the reference uses (no dropout, no residual, no
+row/column scale, no subsets): fp32 math on the rows, one rounding to the input dtype, statistics returned in fp32 -- the
+published contract of the kernel (flash_attn/ops/layer_norm.py:_dropout_add_layer_norm_forward/backward).  With it the UNMODIFIED
+reference runtime runs on the GPU box (oracle/ref_runtime/run_ref.py)."""
+import torch
+
+
+def dropout_add_ln_fwd(x0, residual, gamma, beta, rowscale, colscale, x0_subset, out_subset, dropout_p, epsilon, rowscale_const,
+                       out_numrows, gen, residual_in_fp32, is_rms_norm):
+    assert residual is None and rowscale is None and colscale is None and x0_subset is None and out_subset is None and dropout_p == 0.0, \
+        "shim: only the plain (RMS / layer) norm configuration of the reference is restated"
+    xf = x0.float()
+    if is_rms_norm:
+        mu = torch.zeros(x0.shape[0], dtype=torch.float32, device=x0.device)
+        rsigma = torch.rsqrt(xf.pow(2).mean(-1) + epsilon)
+        z = xf * rsigma[:, None] * gamma.float()
+    else:
+        mu = xf.mean(-1)
+        rsigma = torch.rsqrt((xf - mu[:, None]).pow(2).mean(-1) + epsilon)
+        z = (xf - mu[:, None]) * rsigma[:, None] * gamma.float()
+    if beta is not None:
+        z = z + beta.float()
+    return z.to(x0.dtype), None, None, mu, rsigma
+
+
+def dropout_add_ln_bwd(dz, dx, x, x0, dmask, mu, rsigma, gamma, rowscale, colscale, x0_subset, out_subset, dropout_p, rowscale_const,
+                       x0_numrows, has_residual, is_rms_norm):
+    assert dx is None and dmask is None and rowscale is None and colscale is None and dropout_p == 0.0 and not has_residual
+    xf, g = x.float(), dz.float()
+    xh = xf * rsigma[:, None] if is_rms_norm else (xf - mu[:, None]) * rsigma[:, None]
+    gw = g * gamma.float()
+    if is_rms_norm:
+        dxf = rsigma[:, None] * (gw - xh * (gw * xh).mean(-1, keepdim=True))
+    else:
+        dxf = rsigma[:, None] * (gw - gw.mean(-1, keepdim=True) - xh * (gw * xh).mean(-1, keepdim=True))
+    dgamma = (g * xh).sum(0).to(gamma.dtype)
+    dbeta = g.sum(0).to(gamma.dtype)
+    return dxf.to(x.dtype), None, dgamma, dbeta, None, None
