@@ -61,6 +61,7 @@ def parse():
     p.add_argument("--leg-port", type=int, default=0, help="internal: rendezvous port of the leg")
     p.add_argument("--total-budget-s", type=float, default=760.0, help="wall-clock budget of the whole bench.py run (legs are skipped beyond it)")
     p.add_argument("--no-probe", action="store_true")
+    p.add_argument("--legs-only", action="store_true", help="debug: skip the headline run, run the path legs only (prints {\"path_legs\": ...})")
     return p.parse_args()
 
 
@@ -280,6 +281,14 @@ def run_ours(opts):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)   # bootstrap only (handles, barriers)
     from hetu_galvatron_b200.core.runtime.backend import get_backend, reset_backend
     from hetu_galvatron_b200.core.runtime.utils import get_optimizer_and_param_scheduler
+    if opts.legs_only:
+        legs = run_path_legs(opts, rank, world, local) if world > 1 else []
+        if rank == 0:
+            print(json.dumps({"invalid": "--legs-only: no headline measurement", "n_gpus": world, "path_legs": legs}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     spath, strategy = strategy_for(world, opts.strategy)
     args, config, model = build_model(opts, strategy)
     be = get_backend()

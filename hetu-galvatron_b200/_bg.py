@@ -84,6 +84,7 @@ SIGNATURES = {
     "bg_ce_sumexp": (_i, [_vp, _i, _vp, _vp, _vp, _ll, _ll, _ll, _vp]),
     "bg_ce_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _ll, _ll, _ll, _vp]),
     "bg_gemm_bf16": (_i, [_vp, _vp, _vp, _ll, _ll, _ll, _i, _i, _vp]),
+    "bg_gemm_bf16_add": (_i, [_vp, _vp, _vp, _vp, _ll, _ll, _ll, _i, _vp]),
     "bg_gemm_reduce_scatter": (_i, [_vp, _i, _i, _vp, _vp, _ll, _ll, _ll, _i, _c.POINTER(_sz), _c.POINTER(_sz), _vp, _vp]),
     "bg_gemm_all_reduce": (_i, [_vp, _i, _i, _vp, _vp, _ll, _ll, _ll, _i, _c.POINTER(_sz), _c.POINTER(_sz), _c.POINTER(_sz), _vp]),
     "bg_all_gather_gemm": (_i, [_vp, _i, _i, _vp, _c.POINTER(_sz), _c.POINTER(_sz), _vp, _vp, _ll, _ll, _ll, _i, _vp, _vp]),
@@ -600,6 +601,11 @@ class BgComm:
 def cast(src, dst, scale=1.0, accumulate=False, stream=None):
     check(lib().bg_cast(_ptr(src), dtype_code(src.dtype), _ptr(dst), dtype_code(dst.dtype), src.numel(), float(scale),
                         1 if accumulate else 0, _stream_ptr(stream)))
+
+
+def gemm_bf16_add(a, b, c, addend, m, n, k, layout, stream=None):
+    """C = A op B + addend (residual add in the GEMM epilogue)."""
+    check(lib().bg_gemm_bf16_add(_ptr(a), _ptr(b), _ptr(c), _ptr(addend), int(m), int(n), int(k), int(layout), _stream_ptr(stream)))
 
 
 def gemm_bf16(a, b, c, m, n, k, layout, accumulate=False, stream=None):

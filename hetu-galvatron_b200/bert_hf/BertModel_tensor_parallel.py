@@ -24,10 +24,10 @@ class BertAttention_tp(nn.Module):
 
     def forward(self, hidden_states, attention_mask):
         residual = hidden_states
-        hidden_states, bias = self.attention(hidden_states, attention_mask)
+        hidden_states, bias = self.attention(hidden_states, attention_mask, residual=residual)   # + residual in the GEMM epilogue
         if bias is not None:
             hidden_states = hidden_states + bias
-        return self.LayerNorm(hidden_states + residual)                  # post-LN (:31-39)
+        return self.LayerNorm(hidden_states)                             # post-LN (:31-39)
 
 
 class BertMLP_tp(nn.Module):
@@ -42,10 +42,10 @@ class BertMLP_tp(nn.Module):
 
     def forward(self, hidden_states):
         residual = hidden_states
-        hidden_states, bias = self.mlp(hidden_states)
+        hidden_states, bias = self.mlp(hidden_states, residual=residual)
         if bias is not None:
             hidden_states = hidden_states + bias
-        return self.LayerNorm(hidden_states + residual)
+        return self.LayerNorm(hidden_states)
 
 
 class BertLayer_tp(nn.Module):

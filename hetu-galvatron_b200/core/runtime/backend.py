@@ -434,8 +434,9 @@ class CudaBackend:
         return outs
 
     # ---- math ops --------------------------------------------------------------------------------------------
-    def gemm(self, a, b, layout, out=None, accumulate=False, m=None, n=None, k=None):
-        """bf16 GEMM on tcgen05.  layout 'tn': a[M,K] b[N,K]; 'nn': a[M,K] b[K,N]; 'nt': a[K,M] b[K,N]."""
+    def gemm(self, a, b, layout, out=None, accumulate=False, m=None, n=None, k=None, addend=None):
+        """bf16 GEMM on tcgen05.  layout 'tn': a[M,K] b[N,K]; 'nn': a[M,K] b[K,N]; 'nt': a[K,M] b[K,N].
+        ``addend`` [M,N]: out = A op B + addend in the epilogue (the residual add behind a projection, one rounding)."""
         code = {"tn": 0, "nn": 1, "nt": 2}[layout]
         if code == 2:
             k_, m_ = a.shape
@@ -449,14 +450,20 @@ class CudaBackend:
         assert a.is_contiguous() and b.is_contiguous() and out.is_contiguous()
         if m_ % 8 or n_ % 8 or k_ % 8:
             raise self.bg.BgError("GEMM dims (%d,%d,%d) must be multiples of 8" % (m_, n_, k_))
+        if addend is not None:
+            assert not accumulate and addend.dtype == torch.bfloat16 and addend.is_contiguous() and addend.numel() == m_ * n_
+            launch = lambda: self.bg.gemm_bf16_add(a, b, out, addend, m_, n_, k_, code)  # noqa: E731
+        else:
+            launch = lambda: self.bg.gemm_bf16(a, b, out, m_, n_, k_, code, accumulate=accumulate)  # noqa: E731
         if self.gemm_profile is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            self.bg.gemm_bf16(a, b, out, m_, n_, k_, code, accumulate=accumulate)
+            launch()
             e1.record()
-            self.gemm_profile.append((e0, e1, 2.0 * m_ * n_ * k_, 2.0 * (m_ * k_ + k_ * n_ + m_ * n_ * (2 if accumulate else 1))))
+            extra = 2 if (accumulate or addend is not None) else 1
+            self.gemm_profile.append((e0, e1, 2.0 * m_ * n_ * k_, 2.0 * (m_ * k_ + k_ * n_ + m_ * n_ * extra)))
         else:
-            self.bg.gemm_bf16(a, b, out, m_, n_, k_, code, accumulate=accumulate)
+            launch()
         return out
 
     FUSE_MIN_K = 1536     # measured (profiles/r01_fused_gemm_rs_*): below this the GEMM outruns NVLink and fusion only adds latency

@@ -90,8 +90,11 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, input, weight, sequence_parallel, allreduce_dgrad, allreduce_out, tp_group, reduce_scatter_out=False,
-                recompute_kind=None, recompute_eps=0.0, *recipe):
+                recompute_kind=None, recompute_eps=0.0, addend=None, *recipe):
+        # addend: a tensor of the OUTPUT's shape added to it (the residual of the block: `out + residual`).  When no collective
+        # follows the GEMM it rides in the GEMM epilogue (fp32 accumulator + addend, one rounding, no elementwise pass).
         be = get_backend()
+        ctx.has_addend = addend is not None
         ctx.recompute = (recompute_kind, recompute_eps, len(recipe)) if recompute_kind else None
         if ctx.recompute:
             ctx.save_for_backward(weight, *recipe)
@@ -111,7 +114,8 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
                 staged, _ = be.staging_tensor(tp_group, (x2d.shape[0], n_out), input.dtype)
                 be.gemm(x2d, weight, "tn", out=staged)
                 out = be.reduce_scatter_first_dim(staged, tp_group)
-            return out.view(input.shape[0] // tp_group.size, *input.shape[1:-1], n_out)
+            out = out.view(input.shape[0] // tp_group.size, *input.shape[1:-1], n_out)
+            return out if addend is None else out + addend
         ctx.sequence_parallel = sequence_parallel and multi
         ctx.allreduce_dgrad = allreduce_dgrad and multi
         if ctx.sequence_parallel:
@@ -122,7 +126,8 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
             else:
                 total = be.all_gather_into_staging(input, tp_group)
                 out = be.gemm(total.reshape(-1, total.shape[-1]), weight, "tn")
-            return out.view(*full_shape, n_out)
+            out = out.view(*full_shape, n_out)
+            return out if addend is None else out + addend
         x2d = input.reshape(-1, input.shape[-1])
         if allreduce_out and multi:
             if _can(be, "can_fuse_gemm_ar", x2d.shape[0], n_out, tp_group, x2d.shape[1]):
@@ -131,9 +136,11 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
                 staged, _ = be.staging_tensor(tp_group, (x2d.shape[0], n_out), input.dtype)
                 be.gemm(x2d, weight, "tn", out=staged)
                 out = be.all_reduce(staged, tp_group)
-        else:
-            out = be.gemm(x2d, weight, "tn")
-        return out.view(*input.shape[:-1], n_out)
+            out = out.view(*input.shape[:-1], n_out)
+            return out if addend is None else out + addend
+        if addend is not None:
+            return be.gemm(x2d, weight, "tn", addend=addend.contiguous().reshape(-1, n_out)).view(*input.shape[:-1], n_out)
+        return be.gemm(x2d, weight, "tn").view(*input.shape[:-1], n_out)
 
     @staticmethod
     def backward(ctx, grad_output):
@@ -152,6 +159,7 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
             input, weight = ctx.saved_tensors
         group = ctx.tp_group
         k = weight.shape[1]
+        ctx.saved_grad_output = grad_output if ctx.has_addend else None      # d(out + addend) / d(addend) = identity
         grad_input, dgrad_done, gather_event = None, False, None
         if ctx.reduce_scatter_out:
             # backward of the reduce-scatter is an all-gather along the sequence (mappings_group.py:243-258); the dgrad GEMM
@@ -201,23 +209,24 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
         if gather_event is not None:
             be.wait_event(gather_event)
             grad_weight = _write_wgrad(weight, dy2d, total.reshape(-1, total.shape[-1]))
-        return (grad_input, grad_weight, None, None, None, None, None, None, None) + (None,) * n_recipe
+        grad_addend = ctx.saved_grad_output if ctx.has_addend else None
+        return (grad_input, grad_weight, None, None, None, None, None, None, None, grad_addend) + (None,) * n_recipe
 
 
 def linear_with_grad_accumulation_and_async_allreduce(input, weight, bias=None, gradient_accumulation_fusion=False,
                                                       async_grad_allreduce=False, sequence_parallel=False, tp_group=None,
-                                                      allreduce_out=False, reduce_scatter_out=False, recompute=None):
+                                                      allreduce_out=False, reduce_scatter_out=False, recompute=None, addend=None):
     """Same call shape as layers.py:550-648 (``async_grad_allreduce`` here means "all-reduce dgrad over tp_group").
     ``recompute``: None, ("swiglu", gate_up) or ("rmsnorm", x, norm_weight, eps) -- see the Function's docstring."""
     if recompute is None:
         out = LinearWithGradAccumulationAndAsyncCommunication.apply(input, weight, sequence_parallel, async_grad_allreduce,
-                                                                    allreduce_out, tp_group, reduce_scatter_out)
+                                                                    allreduce_out, tp_group, reduce_scatter_out, None, 0.0, addend)
     else:
         kind = recompute[0]
         eps = float(recompute[3]) if kind == "rmsnorm" else 0.0
         recipe = recompute[1:3] if kind == "rmsnorm" else recompute[1:2]
         out = LinearWithGradAccumulationAndAsyncCommunication.apply(input, weight, sequence_parallel, async_grad_allreduce,
-                                                                    allreduce_out, tp_group, reduce_scatter_out, kind, eps, *recipe)
+                                                                    allreduce_out, tp_group, reduce_scatter_out, kind, eps, addend, *recipe)
     return out if bias is None else out + bias
 
 
@@ -311,21 +320,25 @@ class RowParallelLinear(_ParallelLinearBase):
         else:
             self.register_parameter("bias", None)
 
-    def forward(self, input_, recompute=None):
+    def forward(self, input_, recompute=None, residual=None):
+        """``residual``: added to the output (after the collective; inside the GEMM epilogue when there is none).  Only honoured
+        when this layer adds no bias of its own before it (bias is None or skip_bias_add) -- the callers' contract."""
         if not self.input_is_parallel:
             input_ = scatter_to_tensor_model_parallel_region_group(input_, self.tp_group)
             recompute = None
+        if residual is not None and not self.skip_bias_add and self.bias is not None:
+            raise ValueError("residual fusion needs skip_bias_add (the bias would be added after the residual)")
         if self.sequence_parallel:
             # GEMM and the sequence reduce-scatter (:1109, C8) are one operation: partial tiles go straight to their owner
             out = linear_with_grad_accumulation_and_async_allreduce(
                 input_, self.weight, None, async_grad_allreduce=False, sequence_parallel=False, tp_group=self.tp_group,
-                reduce_scatter_out=True, recompute=recompute)
+                reduce_scatter_out=True, recompute=recompute, addend=residual)
         else:
             # GEMM and the all-reduce of :1110-1114 (C5) are one operation; its backward is the identity, as
             # reduce_from_tensor_model_parallel_region's is (mappings_group.py:142-156)
             out = linear_with_grad_accumulation_and_async_allreduce(
                 input_, self.weight, None, async_grad_allreduce=False, sequence_parallel=False, tp_group=self.tp_group,
-                allreduce_out=True, recompute=recompute)
+                allreduce_out=True, recompute=recompute, addend=residual)
         if not self.skip_bias_add and self.bias is not None:
             out = out + self.bias
         return out, (self.bias if self.skip_bias_add else None)

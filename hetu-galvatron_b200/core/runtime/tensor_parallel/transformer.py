@@ -274,7 +274,8 @@ class ParallelMLP(nn.Module):
         self.dense_4h_to_h = RowParallelLinear(ffn, config.hidden_size, config=config, bias=self.add_bias, input_is_parallel=True,
                                                skip_bias_add=True, tp_group=tp_group, params_dtype=params_dtype, device=device)
 
-    def forward(self, hidden_states, input_recipe=None):
+    def forward(self, hidden_states, input_recipe=None, residual=None):
+        """``residual`` (optional): the block's residual, added to the output inside the last GEMM's epilogue."""
         gate_up, bias = self.dense_h_to_4h(hidden_states, recompute=input_recipe)
         if self.gated:
             if bias is not None:
@@ -283,9 +284,9 @@ class ParallelMLP(nn.Module):
             # --recompute_activations: the 4h->h GEMM keeps gate_up (which SwiGLU's own backward holds anyway) instead of the
             # SwiGLU output and redoes the elementwise pass in backward
             recipe = ("swiglu", gate_up) if _recompute_activations() else None
-            return self.dense_4h_to_h(inter, recompute=recipe)
+            return self.dense_4h_to_h(inter, recompute=recipe, residual=residual)
         inter = _BiasGeluFn.apply(gate_up, bias, self.gelu_tanh)
-        return self.dense_4h_to_h(inter)
+        return self.dense_4h_to_h(inter, residual=residual)
 
 
 class ParallelAttention(nn.Module):
@@ -332,7 +333,7 @@ class ParallelAttention(nn.Module):
         return self._identity_rope[key]
 
     def forward(self, hidden_states, attention_mask=None, encoder_output=None, inference_params=None, rotary_pos_emb=None,
-                input_recipe=None):
+                input_recipe=None, residual=None):
         # hidden_states [sq, b, h]; rotary_pos_emb = (cos, sin) fp32 tables [sq_local, hn/2] for this rank's positions
         mixed, _ = self.query_key_value(hidden_states, recompute=input_recipe)   # [s, b, ng*(r+2)*hn]
         cos, sin = rotary_pos_emb if rotary_pos_emb is not None else self._no_rope(mixed.shape[0], mixed.device)
@@ -357,4 +358,4 @@ class ParallelAttention(nn.Module):
             ctxt = _attention(q, k, v, causal, self.softmax_scale, key_mask)  # [b, s, np, hn]
         b, s = ctxt.shape[0], ctxt.shape[1]
         ctxt = ctxt.reshape(b, s, -1).transpose(0, 1).contiguous()          # "b s h d -> s b (h d)"
-        return self.dense(ctxt)
+        return self.dense(ctxt, residual=residual)

@@ -485,8 +485,23 @@ static int make_ab_maps(CUtensorMap* ma, CUtensorMap* mb, const void* a, const v
     return layout == kTN ? make_map(mb, b, n, k, BLOCK_K, BLOCK_N) : make_map(mb, b, k, n, 64, BLOCK_K);
 }
 
+static int gemm_launch(const void* a, const void* b, void* c, const void* addend, long long m, long long n, long long k, int layout, void* stream);
+
 extern "C" int bg_gemm_bf16(const void* a, const void* b, void* c, long long m, long long n, long long k, int layout,
                             int accumulate, void* stream) {
+    return gemm_launch(a, b, c, accumulate ? c : nullptr, m, n, k, layout, stream);
+}
+
+// C = A op B + addend: the residual add that follows a row-parallel projection (LlamaModel_tensor_parallel.py:83,100: out + residual)
+// rides in the GEMM epilogue -- fp32 accumulator + bf16 addend, ONE rounding, no separate elementwise pass.
+extern "C" int bg_gemm_bf16_add(const void* a, const void* b, void* c, const void* addend, long long m, long long n, long long k,
+                                int layout, void* stream) {
+    if (addend == nullptr || (uintptr_t)addend % 16) return fail(BG_EINVAL, "bg_gemm_bf16_add: addend must be a 16-B aligned [M][N] bf16 tensor");
+    return gemm_launch(a, b, c, addend, m, n, k, layout, stream);
+}
+
+static int gemm_launch(const void* a, const void* b, void* c, const void* addend, long long m, long long n, long long k, int layout, void* stream) {
+    const int accumulate = addend != nullptr;
     if (layout < 0 || layout > 2) return fail(BG_EINVAL, "bg_gemm_bf16: layout %d", layout);
     if (m <= 0 || n <= 0 || k <= 0 || m % 8 || n % 8 || k % 8)
         return fail(BG_EINVAL, "bg_gemm_bf16: m,n,k (%lld,%lld,%lld) must be positive multiples of 8", m, n, k);
@@ -501,7 +516,7 @@ extern "C" int bg_gemm_bf16(const void* a, const void* b, void* c, long long m, 
     const long long tiles = ((m + BLOCK_M - 1) / BLOCK_M) * ((n + BLOCK_N - 1) / BLOCK_N);
     const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
     cudaStream_t st = (cudaStream_t)stream;
-    const __nv_bfloat16* c_old = (const __nv_bfloat16*)c;
+    const __nv_bfloat16* c_old = (const __nv_bfloat16*)addend;
     FuseParams<kPlain> none;
     if (layout == kTN) gemm_bf16_kernel<kTN><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, c_old, (int)m, (int)n, (int)k, accumulate, none);
     else if (layout == kNN) gemm_bf16_kernel<kNN><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mc, c_old, (int)m, (int)n, (int)k, accumulate, none);

@@ -39,10 +39,9 @@ class GPTAttention_tp(nn.Module):
     def forward(self, hidden_states, attention_mask):
         residual = hidden_states
         hidden_states = self.LayerNorm(hidden_states)
-        hidden_states, bias = self.attention(hidden_states, None)      # causal: the mask is implied (flash path, :36-41)
-        if bias is not None:
-            hidden_states = hidden_states + bias
-        return hidden_states + residual
+        # causal: the mask is implied (flash path, :36-41); the residual add (:42) rides in the projection GEMM's epilogue
+        hidden_states, bias = self.attention(hidden_states, None, residual=residual)
+        return hidden_states if bias is None else hidden_states + bias
 
 
 class GPTMLP_tp(nn.Module):
@@ -58,10 +57,8 @@ class GPTMLP_tp(nn.Module):
     def forward(self, hidden_states):
         residual = hidden_states
         hidden_states = self.LayerNorm(hidden_states)
-        hidden_states, bias = self.mlp(hidden_states)
-        if bias is not None:
-            hidden_states = hidden_states + bias
-        return hidden_states + residual
+        hidden_states, bias = self.mlp(hidden_states, residual=residual)
+        return hidden_states if bias is None else hidden_states + bias
 
 
 class GPTLayer_tp(nn.Module):

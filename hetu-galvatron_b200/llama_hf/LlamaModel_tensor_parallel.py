@@ -81,8 +81,9 @@ class LlamaAttention_tp(nn.Module):
         else:
             rope = self._rope(seq, offset, hidden_states.device)
         recipe = ("rmsnorm", residual, self.LayerNorm.weight, self.LayerNorm.eps) if self.recompute_activations else None
-        out, _ = self.attention(hidden_states, attention_mask, rotary_pos_emb=rope, input_recipe=recipe)
-        return out + residual
+        # `out + residual` (:83) rides in the o-proj GEMM's epilogue (or follows its collective)
+        out, _ = self.attention(hidden_states, attention_mask, rotary_pos_emb=rope, input_recipe=recipe, residual=residual)
+        return out
 
 
 class LlamaMLP_tp(nn.Module):
@@ -100,8 +101,8 @@ class LlamaMLP_tp(nn.Module):
         residual = hidden_states
         hidden_states = self.LayerNorm(hidden_states)
         recipe = ("rmsnorm", residual, self.LayerNorm.weight, self.LayerNorm.eps) if self.recompute_activations else None
-        out, _ = self.mlp(hidden_states, input_recipe=recipe)
-        return out + residual
+        out, _ = self.mlp(hidden_states, input_recipe=recipe, residual=residual)      # `out + residual` (:100) in the GEMM epilogue
+        return out
 
 
 class LlamaLayer_tp(nn.Module):

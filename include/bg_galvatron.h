@@ -188,6 +188,10 @@ int bg_ce_bwd(void* logits, int dtype, const long long* target, const float* row
  * 1 = "NN" C = A[M,K] * B[K,N] (dgrad, layers.py:462); 2 = "NT" C = A[K,M]^T * B[K,N] (wgrad, layers.py:534). */
 int bg_gemm_bf16(const void* a, const void* b, void* c, long long m, long long n, long long k, int layout,
                  int accumulate, void* stream);
+/* C = A op B + addend ([M][N] bf16): the residual add behind a projection (llama_hf/LlamaModel_tensor_parallel.py:83,100
+ * `hidden_states + input_tensor`) in the GEMM epilogue -- one rounding, no separate elementwise pass.  addend may alias c. */
+int bg_gemm_bf16_add(const void* a, const void* b, void* c, const void* addend, long long m, long long n, long long k, int layout,
+                     void* stream);
 
 /* C5/C8 fused with K1: C = A op B is computed in 128x256 tcgen05 tiles and REDUCE-SCATTERED along M over the group inside
  * the same operation -- every finished partial tile is TMA-stored into the owning rank's arena (peer HBM over NVLink) and

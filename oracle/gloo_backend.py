@@ -212,11 +212,13 @@ class OracleBackend:
         return outs
 
     # ---- math -------------------------------------------------------------------------------------------------------------------
-    def gemm(self, a, b, layout, out=None, accumulate=False, m=None, n=None, k=None):
+    def gemm(self, a, b, layout, out=None, accumulate=False, m=None, n=None, k=None, addend=None):
         self.launches += 1
         af = a.float().t() if layout == "nt" else a.float()
         bf = b.float().t() if layout == "tn" else b.float()
         res = af @ bf
+        if addend is not None:      # the residual add in the GEMM epilogue: fp32 accumulator + addend, one rounding
+            res = res + addend.float().reshape(res.shape)
         if out is None:
             return res.to(a.dtype)
         out.copy_((res + out.float()).to(out.dtype) if accumulate else res.to(out.dtype))

@@ -69,6 +69,15 @@ def main():
     initialize_model_parallel(tensor_model_parallel_size=1, pipeline_model_parallel_size=1)
     random.model_parallel_cuda_manual_seed(1234)
     args = RuntimeArgs(model_type="llama", rank=rank, checkpoint_dir={"converted": GOLDEN}, backend="hf")
+    # HEAD's test RuntimeArgs predates context parallelism: every option of the runtime's own parser that it lacks gets the
+    # parser's default (galvatron/core/runtime/arguments.py: galvatron_training_args)
+    import argparse as _ap
+    from galvatron.core.runtime.arguments import galvatron_training_args
+    _parser = _ap.ArgumentParser()
+    galvatron_training_args(_parser, use_megatron=False)
+    for k, v in vars(_parser.parse_args([])).items():
+        if not hasattr(args, k):
+            setattr(args, k, v)
     # the tiny Llama of the golden checkpoint, as a dict spec (always with ffn_dim: config_utils.py:33-35)
     args.model_size = {"dim": spec["hidden_size"], "ffn_dim": spec["intermediate_size"], "n_heads": spec["num_attention_heads"],
                        "n_kv_heads": spec["num_key_value_heads"], "n_layers": spec["num_hidden_layers"], "norm_eps": spec["rms_norm_eps"],
@@ -82,8 +91,8 @@ def main():
     args.lr, args.adam_weight_decay = 1e-3, 0.0
     for k, v in over.items():
         setattr(args, k, v)
-    if getattr(args, "use_ulysses", False):
-        args.vocab_sp = 1
+    args.vocab_sp = 1 if getattr(args, "use_ulysses", False) else 0
+    args.micro_batch_size = args.global_train_batch_size
     args.tp_deg = args.global_tp_deg
     set_args(args)
 
