@@ -161,6 +161,7 @@ static long long* tunable(const char* name) {
     if (!strcmp(name, "timeout_ms")) return &g_tun.timeout_ms;
     if (!strcmp(name, "oneshot_bytes")) return &g_tun.oneshot_bytes;
     if (!strcmp(name, "nvls_min_bytes")) return &g_tun.nvls_min_bytes;
+    if (!strcmp(name, "nvls_min_ranks")) return &g_tun.nvls_min_ranks;
     if (!strcmp(name, "nvls_gather")) return &g_tun.nvls_gather;
     if (!strcmp(name, "nvls_reduce")) return &g_tun.nvls_reduce;
     return nullptr;
@@ -514,7 +515,7 @@ int resolve(bg_ctx* c, const Group& g, const size_t* offs, size_t bytes, PeerPtr
 }
 
 char* mc_ptr(bg_ctx* c, int gid, const Group& g, const size_t* offs, size_t bytes) {
-    if (!c->vmm || g.n < 2 || !offs) return nullptr;
+    if (!c->vmm || g.n < 2 || g.n < g_tun.nvls_min_ranks || !offs) return nullptr;
     auto it = c->mc_of.find(gid);
     if (it == c->mc_of.end() || !it->second.bound) return nullptr;
     const bg_ctx::McGroup& m = it->second;

@@ -36,6 +36,7 @@ struct Tunables {
     long long timeout_ms = 60000;  // device-side barrier timeout
     long long oneshot_bytes = 512 * 1024;
     long long nvls_min_bytes = 1 << 20;  // below this the peer-to-peer kernels win (latency)
+    long long nvls_min_ranks = 4;        // groups smaller than this keep the peer-to-peer kernels (measured at p = 2: no gain from the switch)
     long long nvls_gather = 1;     // all-gather / broadcast stores go through the switch (multimem.st) when the buffer is multicast-bound
     long long nvls_reduce = 1;     // reduce-scatter loads are reduced in the switch (multimem.ld_reduce) when the buffer is multicast-bound
 };

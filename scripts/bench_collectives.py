@@ -53,6 +53,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     max_bytes = opts.max_mb << 20
     bg.set_tunable("timeout_ms", 30000)
+    bg.set_tunable("nvls_min_ranks", 2)         # measure the multicast paths at every group size
     nvls = os.environ.get("HGB_NVLS", "1") == "1"
     try:
         comm = bg.BgComm(rank, world, local, 3 * max_bytes + (64 << 20), vmm=nvls)
