@@ -59,6 +59,8 @@ def parse():
     p.add_argument("--legs", default="auto", help="auto (all path legs at N >= 2), none, or a comma-separated list of leg names")
     p.add_argument("--leg", default=None, help="internal: run ONE path leg in this process (spawned per rank by the headline run)")
     p.add_argument("--leg-port", type=int, default=0, help="internal: rendezvous port of the leg")
+    p.add_argument("--kernel-breakdown", default="", help="write a per-kernel time table (torch.profiler/CUPTI, ONE extra untimed step "
+                   "after the measurements; shares only, never a bench value) to this JSON file")
     p.add_argument("--total-budget-s", type=float, default=760.0, help="wall-clock budget of the whole bench.py run (legs are skipped beyond it)")
     p.add_argument("--no-probe", action="store_true")
     p.add_argument("--legs-only", action="store_true", help="debug: skip the headline run, run the path legs only (prints {\"path_legs\": ...})")
@@ -267,6 +269,32 @@ def summarize_comm(prof, steps):
     return out
 
 
+def kernel_breakdown(step_fn, path, ms_per_step):
+    """Where one step goes, kernel by kernel: a CUPTI trace of ONE extra step (after all timed regions).  Taken under a profiler, so
+    only the shares are meaningful; the step time they are compared with is the CUDA-event one."""
+    import collections
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step_fn()
+        torch.cuda.synchronize()
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for ka in prof.key_averages():
+        us = getattr(ka, "self_device_time_total", None)
+        if us is None:
+            us = getattr(ka, "self_cuda_time_total", 0.0)
+        if us > 0:
+            a = agg[ka.key[:110]]
+            a[0] += ka.count
+            a[1] += us
+    rows = sorted(([n, c, round(us / 1e3, 3)] for n, (c, us) in agg.items()), key=lambda r: -r[2])
+    total = sum(r[2] for r in rows)
+    with open(path, "w") as f:
+        json.dump({"what": "torch.profiler (CUPTI) kernel times of one training step; kernels on side streams overlap, so the sum may "
+                           "exceed the step", "event_timed_ms_per_step": round(ms_per_step, 3), "sum_kernel_ms": round(total, 3),
+                   "kernels": [{"name": n, "launches": c, "ms": ms, "share_of_sum": round(ms / total, 4)} for n, c, ms in rows[:60]]}, f, indent=1)
+
+
 def run_ours(opts):
     os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")   # 150+ GiB of long-lived state: avoid fragmentation
     import torch
@@ -370,6 +398,8 @@ def run_ours(opts):
     step(t.to(dev), l.to(dev), it); it += 1
     torch.cuda.synchronize()
     comm, be.comm_profile = summarize_comm(be.comm_profile, 1), None
+    if opts.kernel_breakdown and rank == 0:
+        kernel_breakdown(lambda: step(t.to(dev), l.to(dev), it), opts.kernel_breakdown, ms_res / K)
     gemm_ms = sum(rec[0].elapsed_time(rec[1]) for rec in prof)
     gemm_flops = sum(rec[2] for rec in prof)
     gemm_bytes = sum(rec[3] for rec in prof)
@@ -592,6 +622,8 @@ def run_leg(opts):
     step(W + K)
     torch.cuda.synchronize()
     comm, be.comm_profile = summarize_comm(be.comm_profile, 1), None
+    if opts.kernel_breakdown and rank == 0:
+        kernel_breakdown(lambda: step(t.to(dev), l.to(dev), it), opts.kernel_breakdown, ms_res / K)
     lt = torch.tensor([[x if x is not None else 0.0, 1.0 if x is not None else 0.0] for x in losses], dtype=torch.float64, device=dev)
     dist.all_reduce(lt)                     # the last pipeline stage holds the loss; average the data-parallel replicas
     mean_losses = [round(float(a / max(b, 1.0)), 5) for a, b in lt.tolist()]

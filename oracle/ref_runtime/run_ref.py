@@ -85,7 +85,8 @@ def main():
     args.global_train_batch_size, args.chunks = 4, 1
     args.mixed_precision, args.use_flash_attn = "bf16", True
     args.default_dp_type, args.pipeline_type = "zero2", "pipedream_flush"
-    args.reduce_in_fp32, args.entropy_in_fp32 = False, False          # the runtime's defaults (arguments.py:187,192)
+    # reduce_in_fp32 / entropy_in_fp32 stay True, as the reference's own tests run (tests/utils/runtime_args.py:60-62): the loss is
+    # then resolved to fp32 instead of one bf16 ulp (0.03 at 6.25)
     args.make_vocab_size_divisible_by = 128
     args.untie_embeddings_and_output_weights = True
     args.lr, args.adam_weight_decay = 1e-3, 0.0
@@ -104,19 +105,28 @@ def main():
     dp_idx, dp = dp_ranks.index(rank), len(dp_ranks)
     gbs, seq = args.global_train_batch_size, spec["max_position_embeddings"]
     g = torch.Generator().manual_seed(11)
-    losses = []
+    losses, grad_norms = [], []
     for it in range(opts.steps):
         x = torch.randint(0, spec["vocab_size"], (gbs, seq + 1), generator=g)
         tokens, labels = x[:, :-1].contiguous(), x[:, 1:].contiguous()
         lo, hi = dp_idx * gbs // dp, (dp_idx + 1) * gbs // dp
         loss = model.forward_backward([tokens[lo:hi].to(device)], it, None, loss_func=None, attention_mask=None, labels=labels[lo:hi].to(device))
+        # every rank's local gradient tensors as the optimizer sees them (FSDP: shards under ZeRO-2/3, full copies under DDP; the
+        # tensor-parallel-replicated norm weights once per tp rank), squared and summed over the job
+        sq = torch.zeros((), dtype=torch.float64, device=device)
+        for p in model.parameters():
+            if p.grad is not None:
+                sq += p.grad.detach().double().pow(2).sum()
+        dist.all_reduce(sq)
+        grad_norms.append(float(sq.sqrt()))
         optimizer.step()
         optimizer.zero_grad()
         lt = torch.tensor([loss if loss is not None else 0.0, 1.0 if loss is not None else 0.0], dtype=torch.float64, device=device)
         dist.all_reduce(lt)
         losses.append(float(lt[0] / lt[1]))
     rec = {"case": opts.case, "world": world, "overrides": {k: (v if not isinstance(v, bool) else int(v)) for k, v in over.items()},
-           "losses": losses, "steps": opts.steps, "optimizer": "torch.optim.Adam lr 1e-3 wd 0", "global_batch": gbs, "token_seed": 11,
+           "losses": losses, "grad_norms_all_ranks": grad_norms, "steps": opts.steps, "reduce_in_fp32": int(bool(args.reduce_in_fp32)),
+           "entropy_in_fp32": int(bool(args.entropy_in_fp32)), "optimizer": "torch.optim.Adam lr 1e-3 wd 0", "global_batch": gbs, "token_seed": 11,
            "weights": "tests/golden/ckpt_llama_tiny", "torch": torch.__version__, "gpu": torch.cuda.get_device_name(0),
            "producer": "oracle/ref_runtime/run_ref.py on the unmodified reference runtime (baseline/_ref)"}
     if rank == 0:

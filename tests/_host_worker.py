@@ -227,6 +227,14 @@ def main():
             report["losses"].append(float(lt[0] / lt[1]))
             if it == 1:
                 report["loss_step1"] = report["losses"][-1]       # after one optimizer update: re-gathered parameters
+        # what oracle/ref_runtime/run_ref.py records of the reference runtime: the local gradient tensors of every rank, squared and
+        # summed over the job (shards once, replicated copies once per holder)
+        sq = torch.zeros((), dtype=torch.float64, device=dev)
+        for u in model.model.units:
+            if getattr(u, "master_grad", None) is not None:
+                sq += u.master_grad.detach().double().pow(2).sum()
+        dist.all_reduce(sq)
+        report.setdefault("grad_norms_all_ranks", []).append(float(sq.sqrt()))
         opt.step()
         opt.zero_grad()
     report["n_unshard_2steps"] = [u.n_unshard for u in model.model.units]
