@@ -141,14 +141,29 @@ def ncu_gemm_traffic(flops_per_launch_avg):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def family_of(model):
+    return "gpt" if model.startswith("gpt") else "bert" if model.startswith("bert") else "llama"
+
+
 def build_model(opts, strategy, backend=None):
     import torch
     from hetu_galvatron_b200.core.runtime.arguments import initialize_galvatron
-    from hetu_galvatron_b200.llama_hf import config_from_meta, llama_model_hp, set_model_config
-    from hetu_galvatron_b200.llama_hf.meta_configs import _SPECS
-    spec = dict(_SPECS[opts.model], n_positions=opts.seq)
+    family = family_of(opts.model)
+    if family == "llama":
+        from hetu_galvatron_b200.llama_hf import config_from_meta, llama_model_hp as model_hp, set_model_config
+        from hetu_galvatron_b200.llama_hf.meta_configs import _SPECS
+        seq_key, layers_key = "n_positions", "n_layers"
+    elif family == "gpt":      # galvatron/models/gpt_hf (BASELINE.json configs 1 and 3)
+        from hetu_galvatron_b200.gpt_hf import config_from_meta, gpt_model_hp as model_hp, set_model_config
+        from hetu_galvatron_b200.gpt_hf.meta_configs import _SPECS
+        seq_key, layers_key = "n_positions", "n_layer"
+    else:                      # galvatron/models/bert_hf (BASELINE.json config 4: the sequence length is forced, set_seqlen_manually)
+        from hetu_galvatron_b200.bert_hf import bert_model_hp as model_hp, config_from_meta, set_model_config
+        from hetu_galvatron_b200.bert_hf.meta_configs import _SPECS
+        seq_key, layers_key = "max_position_embeddings", "num_hidden_layers"
+    spec = dict(_SPECS[opts.model], **{seq_key: opts.seq})
     if opts.layers:
-        spec["n_layers"] = opts.layers
+        spec[layers_key] = opts.layers
         n = opts.layers
         for key in ("tp_sizes_enc", "tp_consecutive_flags", "dp_types_enc", "use_sp", "checkpoint", "cp_sizes_enc"):
             if key in strategy:
@@ -169,7 +184,7 @@ def build_model(opts, strategy, backend=None):
                                 recompute_activations=bool(strategy.get("recompute_activations", 0)))
     args.vocab_size = spec["vocab_size"]
     config = set_model_config(config_from_meta(spec), args)
-    model = llama_model_hp(config, args)
+    model = model_hp(config, args)
     return args, config, model
 
 
@@ -191,6 +206,22 @@ def synthetic_batches(args, config, n_steps, dp_idx, dp_size, pin):
             tokens, labels = tokens.pin_memory(), labels.pin_memory()
         out.append((tokens, labels))
     return out
+
+
+def bert_batch(tokens, labels, vocab_size):
+    """DataLoaderForBert semantics (models/bert_hf/dataloader.py:24-120) on top of the seeded token stream: the zero tail of every
+    sample is padding (attention mask 0), the second half of the visible part is segment B, 15 % of the visible tokens carry an
+    MLM label (-100 elsewhere)."""
+    import torch
+    g = torch.Generator().manual_seed(int(tokens[0, :8].sum()) + 7)
+    seq = tokens.shape[1]
+    lengths = (tokens != 0).long().cumsum(1).argmax(1) + 1          # last non-zero position + 1 (padding is the zero tail)
+    lengths = lengths.clamp(min=8)
+    pos = torch.arange(seq)[None, :]
+    mask = pos < lengths[:, None]
+    token_type = ((pos >= (lengths[:, None] // 2)) & mask).long()
+    mlm = torch.where((torch.rand(tokens.shape, generator=g) < 0.15) & mask, tokens, torch.full_like(tokens, -100))
+    return tokens, mlm, mask, token_type
 
 
 NVLINK_NOMINAL_GBS, NVLINK_MEASURED_GBS = 900.0, 770.0    # per direction per GPU; measured = peer copy (B200_PROFILING.md)
@@ -500,11 +531,33 @@ def leg_catalog(n):
         model="llama3-8b", strategy=strat(dp_types_enc=enc(1), checkpoint=enc(1), global_bsz=2 * n, chunks=1, default_dp_type="zero3", embed_sdp=1),
         tiny=dict(sdp=1, global_checkpoint=1, embed_sdp=1, chunks=1, global_train_batch_size=2 * n, zero3_pool_slots=2),
         expect=[], what="C1/C2: ZeRO-3 all-gather (fwd + bwd re-gather) and reduce-scatter+AdamW per layer, pooled buffers, prefetch")
+    # BASELINE.json config 3: GPT-3 6.7B, fixed strategy PP=2 x TP=2 x ZeRO-2 data parallel 2, 1F1B-flush (N = 8; PP2 x TP(N/2) below)
+    d3 = 2 if n == 8 else 1
+    t3 = max(1, n // (2 * d3))
+    legs["gpt-6.7b_pp2_tp%d_zero2dp%d_1f1b" % (t3, d3)] = dict(
+        model="gpt-6.7b", seq=2048,
+        strategy=strat(pp_deg=2, tp_sizes_enc=enc(t3), vtp=t3, global_bsz=8 * d3, chunks=4, pp_division="16,16", default_dp_type="zero2"),
+        tiny=dict(_family="gpt", pp_deg=2, global_tp_deg=t3, vocab_tp=t3, default_dp_type="zero2", chunks=4, pipeline_type="pipedream_flush",
+                  global_train_batch_size=8, _spec=dict(n_positions=128 * t3, n_head=max(4, t3))),
+        expect=[], what="BASELINE config 3: GPT-3 6.7B (gpt_hf family: LayerNorm, bias, GeLU, learned positions), PP2 x TP x ZeRO-2, 1F1B-flush")
+    # BASELINE.json config 4: BERT-large, Ulysses-SP 4 x DP 2, sequence length forced to 8192 (N = 8; Ulysses-SP N below)
+    s4 = 4 if n == 8 else n
+    d4 = n // s4
+    legs["bert-large_ulysses%d_dp%d_seq8192" % (s4, d4)] = dict(
+        model="bert-large", seq=8192,
+        strategy=strat(layers=24, tp_sizes_enc=enc(s4, 24), use_sp=enc(1, 24), vtp=s4, vsp=1, sequence_parallel=1, global_bsz=4 * d4, chunks=2),
+        tiny=dict(_family="bert", global_tp_deg=s4, use_ulysses=True, sequence_parallel=True, vocab_tp=s4, default_dp_type="zero2", chunks=2,
+                  global_train_batch_size=4 * d4, _spec=dict(max_position_embeddings=64 * s4, num_attention_heads=max(4, s4))),
+        expect=[], what="BASELINE config 4: BERT-large (bert_hf family: post-LN, non-causal attention with a padding mask, MLM head), "
+                        "Ulysses all-to-all x data parallel, seq 8192")
     if n == 8:
         legs["llama3-70b_zero3_ckpt_dp8"] = dict(
             model="llama3-70b", strategy=strat(layers=80, dp_types_enc=enc(1, 80), checkpoint=enc(1, 80), global_bsz=8, chunks=1,
                                                default_dp_type="zero3", embed_sdp=1),
             tiny=None, expect=[], what="BASELINE config 5: Llama-3-70B SDP=8 ZeRO-3 + activation checkpointing (>= 0.40 s/step of NVLink time)")
+    if n == 8:      # config 5 before configs 3 and 4: if the wall-clock budget runs out, the later legs are the ones skipped
+        order = [k for k in legs if not k.startswith(("gpt-", "bert-"))] + [k for k in legs if k.startswith(("gpt-", "bert-"))]
+        legs = {k: legs[k] for k in order}
     return legs
 
 
@@ -582,6 +635,8 @@ def run_leg(opts):
     strategy = dict(leg["strategy"])
     lopts = argparse.Namespace(**vars(opts))
     lopts.model, lopts.layers, lopts.checkpoint_layers, lopts.optimizer = leg["model"], 0, -1, "fused"
+    lopts.seq = leg.get("seq", opts.seq)
+    family = family_of(leg["model"])
     t_build = time.time()
     args, config, model = build_model(lopts, strategy)
     be = get_backend()
@@ -593,13 +648,16 @@ def run_leg(opts):
     dp_idx, dp_size = dp_group.rank_in_group(rank), dp_group.size
     K, W = opts.steps, opts.warmup
     host = synthetic_batches(args, config, K + W + 1, dp_idx, dp_size, pin=False)
+    if family == "bert":
+        host = [bert_batch(t, l, config.vocab_size) for t, l in host]
     tokens_per_step = args.global_train_batch_size * config.max_position_embeddings
     it, losses = 0, []
 
     def step(i):
         nonlocal it
-        t, l = host[i]
-        loss = model.forward_backward([t.to(dev)], it, None, loss_func=None, attention_mask=None, labels=l.to(dev))
+        t, l = host[i][:2]
+        extra = dict(attention_mask=None) if family != "bert" else dict(attention_mask=host[i][2].to(dev), token_type_ids=host[i][3].to(dev))
+        loss = model.forward_backward([t.to(dev)], it, None, loss_func=None, labels=l.to(dev), **extra)
         opt.step(); opt.zero_grad()
         it += 1
         return loss
@@ -622,8 +680,6 @@ def run_leg(opts):
     step(W + K)
     torch.cuda.synchronize()
     comm, be.comm_profile = summarize_comm(be.comm_profile, 1), None
-    if opts.kernel_breakdown and rank == 0:
-        kernel_breakdown(lambda: step(t.to(dev), l.to(dev), it), opts.kernel_breakdown, ms_res / K)
     lt = torch.tensor([[x if x is not None else 0.0, 1.0 if x is not None else 0.0] for x in losses], dtype=torch.float64, device=dev)
     dist.all_reduce(lt)                     # the last pipeline stage holds the loss; average the data-parallel replicas
     mean_losses = [round(float(a / max(b, 1.0)), 5) for a, b in lt.tolist()]
@@ -650,12 +706,16 @@ def run_leg(opts):
         for k, v in tiny.pop("_env", {}).items():
             os.environ[k] = v
         os.environ.update(HOST_TEST_CONFIG=json.dumps(tiny), HOST_TEST_BACKEND="cuda", MASTER_PORT=str(opts.leg_port + 1))
-        import _host_worker
+        if family == "llama":
+            import _host_worker as worker
+        else:                       # checker of the GPT / BERT families: oracle/gpt_bert_ref.py (pinned to HF GPT-2 / BERT)
+            import _family_worker as worker
         try:
-            rep = _host_worker.main()
+            rep = worker.main()
             rec["parity"] = {"ok": True, "loss": rep.get("loss"), "oracle_loss": rep.get("ref_loss"), "max_grad_rel_l2": rep.get("max_grad_err"),
                              "worst": rep.get("worst"), "fused_calls": rep.get("fused_calls"), "nvls_groups": rep.get("nvls_groups"),
-                             "criterion": "loss 5e-3 rel, every parameter's gradient 3e-2 rel-L2 vs oracle/llama_ref.py (bf16)"}
+                             "criterion": "loss 5e-3 rel, every parameter's gradient 3e-2 rel-L2 vs oracle/%s (bf16)"
+                                          % ("llama_ref.py" if family == "llama" else "gpt_bert_ref.py")}
         except BaseException as exc:  # noqa: BLE001
             rec["parity"] = {"ok": False, "error": ("%s: %s" % (type(exc).__name__, exc))[:400]}
         if rank == 0:
