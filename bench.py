@@ -637,6 +637,10 @@ def run_leg(opts):
     lopts.model, lopts.layers, lopts.checkpoint_layers, lopts.optimizer = leg["model"], 0, -1, "fused"
     lopts.seq = leg.get("seq", opts.seq)
     family = family_of(leg["model"])
+    # a leg exists to put its kernels under the driver's eyes: the fused GEMM + collective kernels are forced on for the legs that name
+    # them, also at the shapes where the runtime's measured rule (backend.FUSE_MIN_K / FUSE_AR_MIN_K) would pick the unfused pair
+    for k, v in ((leg.get("tiny") or {}).get("_env") or {}).items():
+        os.environ[k] = v
     t_build = time.time()
     args, config, model = build_model(lopts, strategy)
     be = get_backend()

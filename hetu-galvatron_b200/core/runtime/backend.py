@@ -466,7 +466,10 @@ class CudaBackend:
             launch()
         return out
 
-    FUSE_MIN_K = 1536     # measured (profiles/r01_fused_gemm_rs_*): below this the GEMM outruns NVLink and fusion only adds latency
+    # measured (profiles/r01_fused_gemm_rs_4gpu_8gpu.jsonl, r02_fused_gemm_collectives_2gpu.jsonl, r02_fused_8gpu.jsonl): fusion pays when the
+    # GEMM lasts at least as long as the transfer of its output -- K = 3584 at p = 4: 0.226 vs 0.258 ms; below (K = 1792 at p = 8: 0.213 vs
+    # 0.197 unfused) the GEMM outruns NVLink and the fused kernel only adds its reducer tail
+    FUSE_MIN_K = 3072
 
     def can_fuse_gemm_rs(self, m, n, group, k=None):
         p = 1 if group is None else group.size
@@ -478,7 +481,7 @@ class CudaBackend:
         tiles = (m // p // 128) * ((n + 255) // 256)
         return buf is not None and buf.data_bytes >= m * n * 2 and tiles * 4 <= self.FLAG_BYTES // 2
 
-    FUSE_AR_MIN_K = 1024   # as FUSE_MIN_K, for the fused GEMM + all-reduce
+    FUSE_AR_MIN_K = 2048   # as FUSE_MIN_K, for the fused GEMM + all-reduce (wins 9-14 % at K >= 2048, p = 2; loses 6-20 % at K <= 1792, p = 8)
 
     @staticmethod
     def _mnk(a, b, layout):

@@ -884,7 +884,7 @@ extern "C" int bg_gemm_all_reduce(bg_ctx_t c, int gid, int lane, const void* a, 
     s.site = 8;                                   // the reducers' exit barrier
     void* pp[BG_MAX_PEERS]; uint32_t* fp[BG_MAX_PEERS]; void* op[BG_MAX_PEERS];
     for (int i = 0; i < BG_MAX_PEERS; ++i) { pp[i] = partial.p[i]; fp[i] = (uint32_t*)flags.p[i]; op[i] = outs.p[i]; }
-    char* mc = g_tun.nvls_gather ? mc_ptr(c, gid, *g, out_offs, (size_t)m * n * 2) : nullptr;
+    char* mc = g_tun.nvls_bcast ? mc_ptr(c, gid, *g, out_offs, (size_t)m * n * 2) : nullptr;
     rc = bg_gemm_scatter_launch(a, b, m, n, k, layout, g->n, g->me, pp, fp, outs.p[g->me], op, mc,
                                 (unsigned long long)g_tun.timeout_ms * 1000000ull, c->err_dev, st);
     if (rc) return rc;

@@ -164,6 +164,7 @@ static long long* tunable(const char* name) {
     if (!strcmp(name, "nvls_min_ranks")) return &g_tun.nvls_min_ranks;
     if (!strcmp(name, "nvls_gather")) return &g_tun.nvls_gather;
     if (!strcmp(name, "nvls_reduce")) return &g_tun.nvls_reduce;
+    if (!strcmp(name, "nvls_bcast")) return &g_tun.nvls_bcast;
     return nullptr;
 }
 extern "C" int bg_set_tunable(const char* name, long long value) {
@@ -171,7 +172,7 @@ extern "C" int bg_set_tunable(const char* name, long long value) {
     if (!t) return fail(BG_EINVAL, "unknown tunable %s", name ? name : "(null)");
     if (t == &g_tun.comm_ctas && (value < 1 || value > BG_MAX_CHANNELS))
         return fail(BG_EINVAL, "comm_ctas must be in [1,%d]", BG_MAX_CHANNELS);
-    const bool flag = t == &g_tun.nvls_gather || t == &g_tun.nvls_reduce;
+    const bool flag = t == &g_tun.nvls_gather || t == &g_tun.nvls_reduce || t == &g_tun.nvls_bcast;
     if (value < (flag ? 0 : 1)) return fail(BG_EINVAL, "tunable %s must be positive", name);
     *t = value;
     return BG_OK;

@@ -37,7 +37,9 @@ struct Tunables {
     long long oneshot_bytes = 512 * 1024;
     long long nvls_min_bytes = 1 << 20;  // below this the peer-to-peer kernels win (latency)
     long long nvls_min_ranks = 4;        // groups smaller than this keep the peer-to-peer kernels (measured at p = 2: no gain from the switch)
-    long long nvls_gather = 1;     // all-gather / broadcast stores go through the switch (multimem.st) when the buffer is multicast-bound
+    long long nvls_gather = 0;     // all-gather stores through the switch (multimem.st) when the buffer is multicast-bound: measured at
+                                   // p = 8 NOT faster than p peer stores (616 vs 632 GB/s bus at 1 GiB, profiles/r02_collectives_8gpu.jsonl) -> off
+    long long nvls_bcast = 1;      // the fused GEMM + all-reduce reducer writes a summed tile into every member's copy with ONE multimem.st
     long long nvls_reduce = 1;     // reduce-scatter loads are reduced in the switch (multimem.ld_reduce) when the buffer is multicast-bound
 };
 extern Tunables g_tun;

@@ -46,8 +46,9 @@ enum bg_err {
 int bg_abi_version(void);
 const char* bg_last_error(void);                       /* thread-local message of the last failing call */
 /* "comm_ctas" (CTAs of a cross-rank kernel, default 148 = one 128-thread / <=64-register CTA per SM), "local_ctas", "timeout_ms",
- * "oneshot_bytes", "nvls_min_bytes" (multicast paths above this size), "nvls_min_ranks" (... and from this group size on), "nvls_gather" / "nvls_reduce" (0 switches multimem.st /
- * multimem.ld_reduce off for all-gather / reduce-scatter on multicast-bound buffers) */
+ * "oneshot_bytes", "nvls_min_bytes" (multicast paths above this size), "nvls_min_ranks" (... and from this group size on), "nvls_gather" [0] / "nvls_reduce" [1]
+ * (multimem.st for all-gather / multimem.ld_reduce for reduce-scatter on multicast-bound buffers; defaults from the p = 8 measurement),
+ * "nvls_bcast" [1] (the fused GEMM + all-reduce writes a reduced tile to every member with one multimem.st) */
 int bg_set_tunable(const char* name, long long value);
 long long bg_get_tunable(const char* name);
 /* how many kernels this library has launched since load (bench.py's gpu_launches) */
