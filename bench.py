@@ -61,6 +61,8 @@ def parse():
     p.add_argument("--leg-port", type=int, default=0, help="internal: rendezvous port of the leg")
     p.add_argument("--kernel-breakdown", default="", help="write a per-kernel time table (torch.profiler/CUPTI, ONE extra untimed step "
                    "after the measurements; shares only, never a bench value) to this JSON file")
+    p.add_argument("--ncu-step", action="store_true", help="profiling only: after the warm-up run ONE step between cudaProfilerStart/Stop "
+                   "(ncu --profile-from-start off captures exactly that step) and exit without a bench line")
     p.add_argument("--total-budget-s", type=float, default=760.0, help="wall-clock budget of the whole bench.py run (legs are skipped beyond it)")
     p.add_argument("--no-probe", action="store_true")
     p.add_argument("--legs-only", action="store_true", help="debug: skip the headline run, run the path legs only (prints {\"path_legs\": ...})")
@@ -391,6 +393,18 @@ def run_ours(opts):
     for i in range(W):                                         # warm-up (untimed)
         t, l = host[i]
         step(t.to(dev, non_blocking=True), l.to(dev, non_blocking=True), it); it += 1
+
+    if opts.ncu_step:
+        t, l = host[W]
+        t, l = t.to(dev), l.to(dev)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(t, l, it)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        if rank == 0:
+            print(json.dumps({"ncu_step": True, "model": opts.model, "layers": config.num_hidden_layers, "note": "not a bench line"}))
+        return
 
     def timed(resident):
         nonlocal it

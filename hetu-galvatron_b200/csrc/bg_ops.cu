@@ -83,21 +83,38 @@ __global__ void __launch_bounds__(kThreads) cast_kernel(const void* __restrict__
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxVpt = 4;  // register-resident row up to 256 * 8 * 4 = 8192 columns
 
+// VPT = 16-B vectors per thread (1, 2 or 4: the row stays in registers); the NEXT row of the CTA is requested before the current
+// one is reduced, so the loads of a CTA never drain while it sits in the two block-wide barriers.
+template <int VPT>
 __global__ void __launch_bounds__(kThreads) rmsnorm_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w,
                                                                uint4* __restrict__ y, float* __restrict__ rstd_out,
                                                                long long rows, int nvec, float eps) {
     __shared__ float smem[32];
-    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
-        const uint4* xr = x + r * nvec;
-        uint4 xv[kMaxVpt];
+    uint4 cur[VPT], nxt[VPT];
+    long long r = blockIdx.x;
+    if (r < rows) {
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            const int v = threadIdx.x + j * kThreads;
+            if (v < nvec) cur[j] = ld16_stream(x + r * nvec + v);
+        }
+    }
+    for (; r < rows; r += gridDim.x) {
+        const long long rn = r + gridDim.x;
+        if (rn < rows) {
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) {
+                const int v = threadIdx.x + j * kThreads;
+                if (v < nvec) nxt[j] = ld16_stream(x + rn * nvec + v);
+            }
+        }
         float ss = 0.f;
 #pragma unroll
-        for (int j = 0; j < kMaxVpt; ++j) {
-            int v = threadIdx.x + j * kThreads;
+        for (int j = 0; j < VPT; ++j) {
+            const int v = threadIdx.x + j * kThreads;
             if (v < nvec) {
-                xv[j] = ld16_stream(xr + v);
                 float f[8];
-                unpack8(xv[j], f);
+                unpack8(cur[j], f);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
             }
@@ -106,67 +123,90 @@ __global__ void __launch_bounds__(kThreads) rmsnorm_fwd_kernel(const uint4* __re
         const float rstd = rsqrtf(ss / (float)(nvec * 8) + eps);
         if (threadIdx.x == 0 && rstd_out) rstd_out[r] = rstd;
 #pragma unroll
-        for (int j = 0; j < kMaxVpt; ++j) {
-            int v = threadIdx.x + j * kThreads;
+        for (int j = 0; j < VPT; ++j) {
+            const int v = threadIdx.x + j * kThreads;
             if (v < nvec) {
                 float f[8], g[8];
-                unpack8(xv[j], f);
+                unpack8(cur[j], f);
                 unpack8(__ldg(w + v), g);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] = f[i] * rstd * g[i];
                 st16(y + r * nvec + v, pack8(f));
             }
         }
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) cur[j] = nxt[j];
     }
 }
 
 // dx = rstd * (dy*w - xhat * mean(dy*w*xhat)),  dw_partial[cta] = sum over the CTA's rows of dy * xhat
+template <int VPT>
 __global__ void __launch_bounds__(kThreads) rmsnorm_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
                                                                const uint4* __restrict__ w, const float* __restrict__ rstd_in,
                                                                uint4* __restrict__ dx, float* __restrict__ dw_partial,
                                                                long long rows, int nvec) {
     __shared__ float smem[32];
-    float dw[kMaxVpt][8];
+    float dw[VPT][8];
 #pragma unroll
-    for (int j = 0; j < kMaxVpt; ++j)
+    for (int j = 0; j < VPT; ++j)
 #pragma unroll
         for (int i = 0; i < 8; ++i) dw[j][i] = 0.f;
-    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    uint4 cx[VPT], cg[VPT], nx[VPT], ng[VPT];
+    long long r = blockIdx.x;
+    if (r < rows) {
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            const int v = threadIdx.x + j * kThreads;
+            if (v < nvec) { cx[j] = ld16_stream(x + r * nvec + v); cg[j] = ld16_stream(dy + r * nvec + v); }
+        }
+    }
+    for (; r < rows; r += gridDim.x) {
+        const long long rn = r + gridDim.x;
+        if (rn < rows) {
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) {
+                const int v = threadIdx.x + j * kThreads;
+                if (v < nvec) { nx[j] = ld16_stream(x + rn * nvec + v); ng[j] = ld16_stream(dy + rn * nvec + v); }
+            }
+        }
         const float rstd = rstd_in[r];
-        float xh[kMaxVpt][8], gw[kMaxVpt][8];
         float dot = 0.f;
 #pragma unroll
-        for (int j = 0; j < kMaxVpt; ++j) {
-            int v = threadIdx.x + j * kThreads;
+        for (int j = 0; j < VPT; ++j) {
+            const int v = threadIdx.x + j * kThreads;
             if (v < nvec) {
-                float g[8], wv[8];
-                unpack8(ld16_stream(x + r * nvec + v), xh[j]);
-                unpack8(ld16_stream(dy + r * nvec + v), g);
+                float xh[8], g[8], wv[8];
+                unpack8(cx[j], xh);
+                unpack8(cg[j], g);
                 unpack8(__ldg(w + v), wv);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    xh[j][i] *= rstd;
-                    dw[j][i] += g[i] * xh[j][i];
-                    gw[j][i] = g[i] * wv[i];
-                    dot += gw[j][i] * xh[j][i];
+                    xh[i] *= rstd;
+                    dw[j][i] += g[i] * xh[i];
+                    dot += g[i] * wv[i] * xh[i];
                 }
             }
         }
         dot = block_reduce<false>(dot, smem) / (float)(nvec * 8);
 #pragma unroll
-        for (int j = 0; j < kMaxVpt; ++j) {
-            int v = threadIdx.x + j * kThreads;
+        for (int j = 0; j < VPT; ++j) {     // second pass over the packed registers (cheaper than keeping xhat and g*w unpacked)
+            const int v = threadIdx.x + j * kThreads;
             if (v < nvec) {
-                float o[8];
+                float xh[8], g[8], wv[8], o[8];
+                unpack8(cx[j], xh);
+                unpack8(cg[j], g);
+                unpack8(__ldg(w + v), wv);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = rstd * (gw[j][i] - xh[j][i] * dot);
+                for (int i = 0; i < 8; ++i) o[i] = rstd * (g[i] * wv[i] - xh[i] * rstd * dot);
                 st16(dx + r * nvec + v, pack8(o));
             }
         }
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) { cx[j] = nx[j]; cg[j] = ng[j]; }
     }
 #pragma unroll
-    for (int j = 0; j < kMaxVpt; ++j) {
-        int v = threadIdx.x + j * kThreads;
+    for (int j = 0; j < VPT; ++j) {
+        const int v = threadIdx.x + j * kThreads;
         if (v < nvec) {
             float4* d = reinterpret_cast<float4*>(dw_partial + ((size_t)blockIdx.x * nvec + v) * 8);
             d[0] = make_float4(dw[j][0], dw[j][1], dw[j][2], dw[j][3]);
@@ -344,37 +384,60 @@ __global__ void __launch_bounds__(kThreads) bias_gelu_kernel(const uint4* __rest
 // ---------------------------------------------------------------------------------------------
 // swiglu: gate_up = [rows, 2*ffn] (gate = first half, up = second; transformer.py:122-124)
 // ---------------------------------------------------------------------------------------------
+// grid = (column blocks of a row, row groups): no index division; two rows per iteration = four 16-B loads in flight per thread
 __global__ void __launch_bounds__(kThreads) swiglu_fwd_kernel(const uint4* __restrict__ gu, uint4* __restrict__ y,
                                                               long long rows, int fvec) {
-    const size_t total = (size_t)rows * fvec, stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const size_t r = i / fvec, c = i - r * fvec;
+    const int c = blockIdx.x * kThreads + threadIdx.x;
+    if (c >= fvec) return;
+    const long long step = gridDim.y;
+    for (long long r = blockIdx.y; r < rows; r += 2 * step) {
+        const long long r2 = r + step;
+        const bool two = r2 < rows;
+        const uint4 g0 = ld16_stream(gu + r * 2 * fvec + c), u0 = ld16_stream(gu + r * 2 * fvec + fvec + c);
+        uint4 g1 = g0, u1 = u0;
+        if (two) { g1 = ld16_stream(gu + r2 * 2 * fvec + c); u1 = ld16_stream(gu + r2 * 2 * fvec + fvec + c); }
         float g[8], u[8];
-        unpack8(ld16_stream(gu + r * 2 * fvec + c), g);
-        unpack8(ld16_stream(gu + r * 2 * fvec + fvec + c), u);
+        unpack8(g0, g); unpack8(u0, u);
 #pragma unroll
         for (int k = 0; k < 8; ++k) g[k] = g[k] / (1.f + __expf(-g[k])) * u[k];
-        st16(y + i, pack8(g));
+        st16(y + r * fvec + c, pack8(g));
+        if (two) {
+            unpack8(g1, g); unpack8(u1, u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[k] = g[k] / (1.f + __expf(-g[k])) * u[k];
+            st16(y + r2 * fvec + c, pack8(g));
+        }
     }
 }
 
 __global__ void __launch_bounds__(kThreads) swiglu_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ gu,
                                                               uint4* __restrict__ dgu, long long rows, int fvec) {
-    const size_t total = (size_t)rows * fvec, stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const size_t r = i / fvec, c = i - r * fvec;
-        float g[8], u[8], d[8], dg[8], du[8];
-        unpack8(ld16_stream(gu + r * 2 * fvec + c), g);
-        unpack8(ld16_stream(gu + r * 2 * fvec + fvec + c), u);
-        unpack8(ld16_stream(dy + i), d);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float sg = 1.f / (1.f + __expf(-g[k]));
-            du[k] = d[k] * g[k] * sg;
-            dg[k] = d[k] * u[k] * sg * (1.f + g[k] * (1.f - sg));
+    const int c = blockIdx.x * kThreads + threadIdx.x;
+    if (c >= fvec) return;
+    const long long step = gridDim.y;
+    for (long long r = blockIdx.y; r < rows; r += 2 * step) {
+        const long long r2 = r + step;
+        const bool two = r2 < rows;
+        const uint4 g0 = ld16_stream(gu + r * 2 * fvec + c), u0 = ld16_stream(gu + r * 2 * fvec + fvec + c), d0 = ld16_stream(dy + r * fvec + c);
+        uint4 g1 = g0, u1 = u0, d1 = d0;
+        if (two) {
+            g1 = ld16_stream(gu + r2 * 2 * fvec + c); u1 = ld16_stream(gu + r2 * 2 * fvec + fvec + c); d1 = ld16_stream(dy + r2 * fvec + c);
         }
-        st16(dgu + r * 2 * fvec + c, pack8(dg));
-        st16(dgu + r * 2 * fvec + fvec + c, pack8(du));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !two) break;
+            const long long rr = h ? r2 : r;
+            float g[8], u[8], d[8], dg[8], du[8];
+            unpack8(h ? g1 : g0, g); unpack8(h ? u1 : u0, u); unpack8(h ? d1 : d0, d);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float sg = 1.f / (1.f + __expf(-g[k]));
+                du[k] = d[k] * g[k] * sg;
+                dg[k] = d[k] * u[k] * sg * (1.f + g[k] * (1.f - sg));
+            }
+            st16(dgu + rr * 2 * fvec + c, pack8(dg));
+            st16(dgu + rr * 2 * fvec + fvec + c, pack8(du));
+        }
     }
 }
 
@@ -384,46 +447,76 @@ __global__ void __launch_bounds__(kThreads) swiglu_bwd_kernel(const uint4* __res
 // q: [b, s, ng*r, hn]   k, v: [b, s, ng, hn]   cos/sin: [s, hn/2] fp32 (already offset for this rank)
 // forward: q,k rotated by (+theta); backward: reads dq,dk,dv and writes dmixed rotated by (-theta).
 // ---------------------------------------------------------------------------------------------
+// One CTA walks tokens (s, b); a thread owns the same (group, head, half-head vector) of every token it visits, so the index
+// decomposition is done once, outside the token loop, and all loads of a token are issued before the first use.
+constexpr int kRopePairs = 2;   // (lo, hi) vector pairs per thread and token: covers ng * (r + 2) * hn / 16 <= 512 pairs (8192 columns)
 __global__ void __launch_bounds__(kThreads) qkv_rope_kernel(uint4* __restrict__ mixed, uint4* __restrict__ q,
                                                             uint4* __restrict__ k, uint4* __restrict__ v,
                                                             const float* __restrict__ cos_t, const float* __restrict__ sin_t,
                                                             long long s, long long b, int ng, int r, int hn, int backward) {
     const int half_vec = hn / 16;              // 16-B vectors in half a head
     const int heads = r + 2;
-    const size_t total = (size_t)s * b * ng * heads * half_vec, stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        size_t t = i;
-        const int c = (int)(t % half_vec); t /= half_vec;
-        const int j = (int)(t % heads); t /= heads;
-        const int g = (int)(t % ng); t /= ng;
-        const long long bi = (long long)(t % b), si = (long long)(t / b);
-        // mixed vector index of the first half of this head
-        const size_t m0 = ((((size_t)si * b + bi) * ng + g) * heads + j) * (2 * half_vec) + c;
-        uint4* dst_base;
-        size_t o0;
-        if (j < r) { dst_base = q; o0 = ((((size_t)bi * s + si) * ng + g) * r + j) * (2 * half_vec) + c; }
-        else { dst_base = (j == r) ? k : v; o0 = (((size_t)bi * s + si) * ng + g) * (2 * half_vec) + c; }
-        uint4* src_lo = backward ? dst_base + o0 : mixed + m0;
-        uint4* dst_lo = backward ? mixed + m0 : dst_base + o0;
-        float lo[8], hi[8];
-        unpack8(ld16_stream(src_lo), lo);
-        unpack8(ld16_stream(src_lo + half_vec), hi);
-        if (j <= r) {  // q and k heads are rotated, v is copied
-            const float4* cp = reinterpret_cast<const float4*>(cos_t + si * (hn / 2) + c * 8);
-            const float4* sp = reinterpret_cast<const float4*>(sin_t + si * (hn / 2) + c * 8);
-            float4 c0 = __ldg(cp), c1 = __ldg(cp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
-            const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-            float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const int pairs = ng * heads * half_vec;   // per token
+    int pc[kRopePairs], pj[kRopePairs];
+    size_t pm[kRopePairs], po[kRopePairs];     // offsets inside a token of the mixed row / of the destination row
+    for (int e = 0; e < kRopePairs; ++e) {
+        const int p = threadIdx.x + e * kThreads;
+        const int c = p % half_vec, j = (p / half_vec) % heads, g = p / (half_vec * heads);
+        pc[e] = c; pj[e] = p < pairs ? j : -1;
+        pm[e] = ((size_t)g * heads + j) * (2 * half_vec) + c;
+        po[e] = (j < r) ? ((size_t)g * r + j) * (2 * half_vec) + c : (size_t)g * (2 * half_vec) + c;
+    }
+    const size_t mixed_tok = (size_t)pairs * 2, q_tok = (size_t)ng * r * 2 * half_vec, kv_tok = (size_t)ng * 2 * half_vec;
+    const long long tokens = s * b;
+    for (int base = 0; base < pairs; base += kRopePairs * kThreads) {   // rows wider than kRopePairs * kThreads pairs: extra passes
+        for (long long t = blockIdx.x; t < tokens; t += gridDim.x) {
+            const long long si = t / b, bi = t - si * b;
+            const size_t tok_out = (size_t)bi * s + si;                // q/k/v are [b, s, ...]
+            uint4 lo4[kRopePairs], hi4[kRopePairs];
+            uint4* dst[kRopePairs];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float sg = backward ? -sn[e] : sn[e];
-                const float a = lo[e], bb = hi[e];
-                lo[e] = a * cs[e] - bb * sg;   // t*cos + rotate_half(t)*sin, rotate_half = (-x2, x1)
-                hi[e] = bb * cs[e] + a * sg;
+            for (int e = 0; e < kRopePairs; ++e) {
+                if (pj[e] < 0) continue;
+                uint4* m = mixed + (size_t)t * mixed_tok + pm[e];
+                uint4* o = (pj[e] < r) ? q + tok_out * q_tok + po[e] : ((pj[e] == r) ? k : v) + tok_out * kv_tok + po[e];
+                uint4* src = backward ? o : m;
+                dst[e] = backward ? m : o;
+                lo4[e] = ld16_stream(src);
+                hi4[e] = ld16_stream(src + half_vec);
+            }
+#pragma unroll
+            for (int e = 0; e < kRopePairs; ++e) {
+                if (pj[e] < 0) continue;
+                float lo[8], hi[8];
+                unpack8(lo4[e], lo);
+                unpack8(hi4[e], hi);
+                if (pj[e] <= r) {  // q and k heads are rotated, v is copied
+                    const float4* cp = reinterpret_cast<const float4*>(cos_t + si * (hn / 2) + pc[e] * 8);
+                    const float4* sp = reinterpret_cast<const float4*>(sin_t + si * (hn / 2) + pc[e] * 8);
+                    float4 c0 = __ldg(cp), c1 = __ldg(cp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
+                    const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                    const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float sg = backward ? -sn[i] : sn[i];
+                        const float a = lo[i], bb = hi[i];
+                        lo[i] = a * cs[i] - bb * sg;   // t*cos + rotate_half(t)*sin, rotate_half = (-x2, x1)
+                        hi[i] = bb * cs[i] + a * sg;
+                    }
+                }
+                st16(dst[e], pack8(lo));
+                st16(dst[e] + half_vec, pack8(hi));
             }
         }
-        st16(dst_lo, pack8(lo));
-        st16(dst_lo + half_vec, pack8(hi));
+        if (base + kRopePairs * kThreads < pairs) {   // next pass: shift this thread's pairs
+            for (int e = 0; e < kRopePairs; ++e) {
+                const int p = threadIdx.x + e * kThreads + base + kRopePairs * kThreads;
+                const int c = p % half_vec, j = (p / half_vec) % heads, g = p / (half_vec * heads);
+                pc[e] = c; pj[e] = p < pairs ? j : -1;
+                pm[e] = ((size_t)g * heads + j) * (2 * half_vec) + c;
+                po[e] = (j < r) ? ((size_t)g * r + j) * (2 * half_vec) + c : (size_t)g * (2 * half_vec) + c;
+            }
+        }
     }
 }
 
@@ -551,8 +644,10 @@ extern "C" int bg_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd
     if (!BG_ALIGNED16(x) || !BG_ALIGNED16(w) || !BG_ALIGNED16(y)) return fail(BG_EINVAL, "bg_rmsnorm_fwd: 16-B alignment");
     if (rows == 0) return BG_OK;
     int grid = (int)(rows < g_tun.local_ctas ? rows : g_tun.local_ctas);
-    rmsnorm_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)w, (uint4*)y, rstd, rows,
-                                                                    (int)(cols / 8), eps);
+    const int nvec = (int)(cols / 8), vpt = (nvec + kThreads - 1) / kThreads;
+#define BG_RMS_FWD(V) rmsnorm_fwd_kernel<V><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)w, (uint4*)y, rstd, rows, nvec, eps)
+    if (vpt <= 1) BG_RMS_FWD(1); else if (vpt == 2) BG_RMS_FWD(2); else BG_RMS_FWD(4);
+#undef BG_RMS_FWD
     BG_CHECK_LAUNCH();
     return BG_OK;
 }
@@ -564,18 +659,29 @@ extern "C" int bg_rmsnorm_bwd(const void* dy, const void* x, const void* w, cons
     if (n_partial < 1) return fail(BG_EINVAL, "bg_rmsnorm_bwd: n_partial must be >= 1");
     if (!BG_ALIGNED16(dy) || !BG_ALIGNED16(x) || !BG_ALIGNED16(w) || !BG_ALIGNED16(dx) || !BG_ALIGNED16(dw_partial))
         return fail(BG_EINVAL, "bg_rmsnorm_bwd: 16-B alignment");
-    rmsnorm_bwd_kernel<<<n_partial, kThreads, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint4*)x, (const uint4*)w, rstd,
-                                                                         (uint4*)dx, dw_partial, rows, (int)(cols / 8));
+    const int nvec = (int)(cols / 8), vpt = (nvec + kThreads - 1) / kThreads;
+#define BG_RMS_BWD(V) rmsnorm_bwd_kernel<V><<<n_partial, kThreads, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint4*)x, (const uint4*)w, rstd, (uint4*)dx, dw_partial, rows, nvec)
+    if (vpt <= 1) BG_RMS_BWD(1); else if (vpt == 2) BG_RMS_BWD(2); else BG_RMS_BWD(4);
+#undef BG_RMS_BWD
     BG_CHECK_LAUNCH();
     return BG_OK;
+}
+
+// (column blocks, row groups): about local_ctas CTAs in total, every CTA visiting >= 2 rows when there are enough of them
+static dim3 swiglu_grid(long long rows, long long fvec) {
+    const long long cb = (fvec + kThreads - 1) / kThreads;
+    long long gy = g_tun.local_ctas / cb;
+    if (gy < 1) gy = 1;
+    if (gy > (rows + 1) / 2) gy = (rows + 1) / 2;
+    if (gy > 65535) gy = 65535;
+    return dim3((unsigned)cb, (unsigned)gy, 1);
 }
 
 extern "C" int bg_swiglu_fwd(const void* gate_up, void* y, long long rows, long long ffn, void* stream) {
     if (ffn <= 0 || ffn % 8) return fail(BG_EINVAL, "bg_swiglu_fwd: ffn %lld must be a multiple of 8", ffn);
     if (!BG_ALIGNED16(gate_up) || !BG_ALIGNED16(y)) return fail(BG_EINVAL, "bg_swiglu_fwd: 16-B alignment");
     if (rows == 0) return BG_OK;
-    swiglu_fwd_kernel<<<local_grid((size_t)rows * ffn / 8, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-        (const uint4*)gate_up, (uint4*)y, rows, (int)(ffn / 8));
+    swiglu_fwd_kernel<<<swiglu_grid(rows, ffn / 8), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)gate_up, (uint4*)y, rows, (int)(ffn / 8));
     BG_CHECK_LAUNCH();
     return BG_OK;
 }
@@ -584,8 +690,8 @@ extern "C" int bg_swiglu_bwd(const void* dy, const void* gate_up, void* dgate_up
     if (ffn <= 0 || ffn % 8) return fail(BG_EINVAL, "bg_swiglu_bwd: ffn %lld must be a multiple of 8", ffn);
     if (!BG_ALIGNED16(dy) || !BG_ALIGNED16(gate_up) || !BG_ALIGNED16(dgate_up)) return fail(BG_EINVAL, "bg_swiglu_bwd: 16-B alignment");
     if (rows == 0) return BG_OK;
-    swiglu_bwd_kernel<<<local_grid((size_t)rows * ffn / 8, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-        (const uint4*)dy, (const uint4*)gate_up, (uint4*)dgate_up, rows, (int)(ffn / 8));
+    swiglu_bwd_kernel<<<swiglu_grid(rows, ffn / 8), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint4*)gate_up, (uint4*)dgate_up, rows,
+                                                                                       (int)(ffn / 8));
     BG_CHECK_LAUNCH();
     return BG_OK;
 }
@@ -598,7 +704,8 @@ extern "C" int bg_qkv_rope(void* mixed, void* q, void* k, void* v, const float* 
         return fail(BG_EINVAL, "bg_qkv_rope: 16-B alignment");
     const size_t total = (size_t)s * b * ng * (r + 2) * (hn / 16);
     if (total == 0) return BG_OK;
-    qkv_rope_kernel<<<local_grid(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+    const long long tokens = s * b;
+    qkv_rope_kernel<<<(int)(tokens < g_tun.local_ctas ? tokens : g_tun.local_ctas), kThreads, 0, (cudaStream_t)stream>>>(
         (uint4*)mixed, (uint4*)q, (uint4*)k, (uint4*)v, cos_t, sin_t, s, b, (int)ng, (int)r, (int)hn, backward);
     BG_CHECK_LAUNCH();
     return BG_OK;
@@ -689,7 +796,7 @@ extern "C" int bg_bias_gelu(const void* x, const void* bias, const void* dy, voi
 int bg_preload_ops() {
 #define K(f) reinterpret_cast<const void*>(&f)
     const void* kernels[] = {K((cast_kernel<true, true>)), K((cast_kernel<true, false>)), K((cast_kernel<false, true>)), K((cast_kernel<false, false>)),
-                             K(rmsnorm_fwd_kernel), K(rmsnorm_bwd_kernel), K(layernorm_fwd_kernel), K(layernorm_bwd_kernel),
+                             K(rmsnorm_fwd_kernel<1>), K(rmsnorm_fwd_kernel<2>), K(rmsnorm_fwd_kernel<4>), K(rmsnorm_bwd_kernel<1>), K(rmsnorm_bwd_kernel<2>), K(rmsnorm_bwd_kernel<4>), K(layernorm_fwd_kernel), K(layernorm_bwd_kernel),
                              K((bias_gelu_kernel<true, false>)), K((bias_gelu_kernel<false, false>)), K((bias_gelu_kernel<true, true>)),
                              K((bias_gelu_kernel<false, true>)), K(swiglu_fwd_kernel), K(swiglu_bwd_kernel), K(qkv_rope_kernel),
                              K(ce_rowmax_kernel<true>), K(ce_rowmax_kernel<false>), K(ce_sumexp_kernel<true>), K(ce_sumexp_kernel<false>),

@@ -52,7 +52,7 @@ def test_cast(bg, n, scale, acc, sd, dd):
         close_bf16(dst, want) if dd == BF else torch.testing.assert_close(dst, want, rtol=1e-6, atol=1e-6)
 
 
-@pytest.mark.parametrize("rows,cols", [(1, 8), (37, 128), (1000, 4096), (64, 8192)])
+@pytest.mark.parametrize("rows,cols", [(1, 8), (37, 128), (1000, 4096), (64, 8192), (50, 3072), (301, 5120), (2500, 2048)])
 def test_rmsnorm_fwd_bwd(bg, rows, cols):
     x = torch.randn(rows, cols, device="cuda").to(BF)
     w = (1 + 0.1 * torch.randn(cols, device="cuda")).to(BF)
@@ -73,7 +73,7 @@ def test_rmsnorm_fwd_bwd(bg, rows, cols):
     torch.testing.assert_close(dwp.sum(0), wf.grad, rtol=2e-3, atol=2e-2 * (rows ** 0.5) / 30 + 1e-3)
 
 
-@pytest.mark.parametrize("rows,ffn", [(1, 8), (33, 256), (2048, 14336)])
+@pytest.mark.parametrize("rows,ffn", [(1, 8), (33, 256), (2048, 14336), (3, 1792), (4097, 3584)])
 def test_swiglu(bg, rows, ffn):
     gu = torch.randn(rows, 2 * ffn, device="cuda").to(BF)
     dy = torch.randn(rows, ffn, device="cuda").to(BF)
@@ -107,7 +107,7 @@ def _ref_qkv_rope(mixed, cos, sin, ng, r, hn):
     return [t.permute(1, 0, 2, 3).contiguous() for t in (q, k, v)]
 
 
-@pytest.mark.parametrize("s,b,ng,r,hn", [(16, 1, 1, 1, 16), (64, 2, 2, 4, 64), (512, 1, 8, 4, 128)])
+@pytest.mark.parametrize("s,b,ng,r,hn", [(16, 1, 1, 1, 16), (64, 2, 2, 4, 64), (512, 1, 8, 4, 128), (40, 2, 16, 4, 128), (3000, 1, 1, 4, 128)])
 def test_qkv_rope_fwd_bwd(bg, s, b, ng, r, hn):
     from oracle.collectives_ref import rope_tables
     mixed = torch.randn(s, b, ng * (r + 2) * hn, device="cuda").to(BF)
