@@ -735,7 +735,8 @@ def run_leg(opts):
                              "criterion": "loss 5e-3 rel, every parameter's gradient 3e-2 rel-L2 vs oracle/%s (bf16)"
                                           % ("llama_ref.py" if family == "llama" else "gpt_bert_ref.py")}
         except BaseException as exc:  # noqa: BLE001
-            rec["parity"] = {"ok": False, "error": ("%s: %s" % (type(exc).__name__, exc))[:400]}
+            import traceback
+            rec["parity"] = {"ok": False, "error": ("%s: %s" % (type(exc).__name__, exc))[:400], "traceback_tail": traceback.format_exc()[-900:]}
         if rank == 0:
             print("LEG_JSON " + json.dumps(rec), flush=True)
         if not rec["parity"]["ok"]:

@@ -86,7 +86,10 @@ def main():
     golden_ckpt, save_to = over.pop("_golden_ckpt", None), over.pop("_save_to", None)
     save_after, n_iters, skip_batches = over.pop("_save_after", 0), over.pop("_iters", 2), over.pop("_skip_batches", 0)
     clip = over.pop("_clip_grad", None)
+    budget_tol = over.pop("_budget", None)
     use_cuda = os.environ.get("HOST_TEST_BACKEND", "oracle") == "cuda"
+    if budget_tol is None:      # observed on the CPU corpus: 1.02-1.27 up to 4 ranks, 1.15-1.69 at 8 (tensor-parallel 8: eight bf16 partials per sum)
+        budget_tol = (2.0 if world >= 8 else 1.5) if not use_cuda else 2.5
     from oracle import llama_ref
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import smoke_model as sm
@@ -189,6 +192,24 @@ def main():
             for i, (gl, wl) in enumerate(zip(got["layers"], w["layers"])):
                 for k in gl:
                     errs["%s%d" % (k, i)] = rel(gl[k], wl[k].grad * scale["gpt_dec_%d" % (i + 1)])
+            # error budget: the same gradients in fp64 (on the bf16-rounded weights the model computes with) are the truth; the
+            # product may be at most ``_budget`` x as far from it as the bf16 single-process oracle is, parameter by parameter
+            # (a floor of 2e-3 keeps tiny denominators out) -- what lets the blanket 3e-2 above be read as "bf16 noise"
+            w64 = {k: (v.detach().bfloat16().double().requires_grad_(True) if torch.is_tensor(v) else
+                       [{kk: vv.detach().bfloat16().double().requires_grad_(True) for kk, vv in lw.items()} for lw in v]) for k, v in w.items()}
+            _, loss64 = llama_ref.forward_loss(w64, tokens, labels, cfg, dtype=torch.float64)
+            loss64.backward()
+            budget = {"embed": (rel(got["embed"], w64["embed"].grad * scale["embed_0"]), rel(w["embed"].grad, w64["embed"].grad)),
+                      "lm_head": (rel(got["lm_head"], w64["lm_head"].grad * scale["cls_%d" % (L + 2)]), rel(w["lm_head"].grad, w64["lm_head"].grad)),
+                      "norm": (rel(got["norm"], w64["norm"].grad * scale["norm_%d" % (L + 1)]), rel(w["norm"].grad, w64["norm"].grad))}
+            for i, (gl, wl, wl64) in enumerate(zip(got["layers"], w["layers"], w64["layers"])):
+                for k in gl:
+                    budget["%s%d" % (k, i)] = (rel(gl[k], wl64[k].grad * scale["gpt_dec_%d" % (i + 1)]), rel(wl[k].grad, wl64[k].grad))
+            ratios = {k: a / max(b, 2e-3) for k, (a, b) in budget.items()}
+            worst_b = max(ratios, key=ratios.get)
+            report.update({"err_budget_ratio": ratios[worst_b], "err_budget_worst": worst_b, "err_vs_fp64_ours": budget[worst_b][0],
+                           "err_vs_fp64_oracle_bf16": budget[worst_b][1], "max_err_vs_fp64_ours": max(a for a, _ in budget.values()),
+                           "max_err_vs_fp64_oracle_bf16": max(b for _, b in budget.values())})
             # loss: the last pipeline stage holds it; average the data-parallel replicas
             lt = torch.tensor([loss if loss is not None else 0.0, 1.0 if loss is not None else 0.0], dtype=torch.float64, device=dev)
             dist.all_reduce(lt)
@@ -210,6 +231,7 @@ def main():
                     print("DEBUG layer", i, "scale", scale["gpt_dec_%d" % (i + 1)], {k: fit(gl[k], wl[k].grad) for k in gl}, flush=True)
             assert abs(mean_loss - float(ref_loss)) <= 5e-3 * abs(float(ref_loss)), report
             assert report["max_grad_err"] < tol, (report, errs)
+            assert report["err_budget_ratio"] <= budget_tol, report
             if clip is not None:
                 # clip_grad_norm (core/runtime/utils.py:124-133): the job-wide L2 norm counts every parameter once -- the oracle's
                 # gradients of the un-parallelised model give the expected value -- and every shard is scaled by the same factor

@@ -52,4 +52,5 @@ CASES = {
 def test_family(name):
     world, cfg = CASES[name]
     rep = launch(world, dict(cfg))
-    assert rep["max_grad_err"] < 3e-2 and rep["loss_step1"] < rep["loss"]
+    assert rep["max_grad_err"] < 3e-2
+    assert abs(rep["loss_step1"] - rep["ref_loss_step1"]) <= 5e-3 * abs(rep["ref_loss_step1"])     # after one AdamW step, vs the oracle's

@@ -125,6 +125,33 @@ def test_families_two_gpus(name):
     assert rep["max_grad_err"] < 3e-2 and rep["launches"] > 0
 
 
+def _leg_names(n):
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return {k: v for k, v in mod.leg_catalog(n).items() if v["tiny"] is not None}
+
+
+@pytest.mark.parametrize("name", sorted(_leg_names(2)))
+def test_bench_leg_tiny_strategies_two_gpus(name):
+    """the tiny-model twin of every bench.py path leg (the run whose verdict the leg reports as ``parity``) on the product path"""
+    _need(2)
+    import json
+    from test_families import launch as launch_family
+    tiny = json.loads(json.dumps(_leg_names(2)[name]["tiny"]))
+    env = tiny.pop("_env", {})
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        rep = (launch_family if "_family" in tiny else launch)(2, tiny, backend="cuda")
+    finally:
+        for k, v in old.items():
+            os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+    assert rep["max_grad_err"] < 3e-2 and rep["launches"] > 0
+
+
 @pytest.mark.parametrize("name", ["gpt_baseline3_pp2_tp2_sp_zero2", "bert_baseline4_ulysses2_dp2"])
 def test_families_four_gpus(name):
     """BASELINE.json configs 3 and 4 at the tiny model's size: GPT PP2 x TP2 x ZeRO-2 1F1B, BERT Ulysses x DP."""

@@ -181,7 +181,13 @@ def test_world4(name):
     assert rep["max_grad_err"] < 3e-2
 
 
-@pytest.mark.parametrize("name", sorted(WORLD8))
+# the reference's hybrid corpus always; of its six redistributed cases one by default and all with HGB_SLOW_TESTS=1 (15 s each on CPU;
+# the GPU suite, tests/test_gpu_model.py, always runs all of them)
+_WORLD8_DEFAULT = [n for n in sorted(WORLD8) if not n.startswith("ref_redistributed") or n == "ref_redistributed_tp1248_vtp8_sp"
+                   or os.environ.get("HGB_SLOW_TESTS")]
+
+
+@pytest.mark.parametrize("name", _WORLD8_DEFAULT)
 def test_world8(name):
     rep = launch(8, dict(WORLD8[name]), timeout=900)
     assert rep["max_grad_err"] < 3e-2
