@@ -49,11 +49,19 @@ def main():
     ap.add_argument("--case", required=True, choices=sorted(CASES))
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out"))
     ap.add_argument("--steps", type=int, default=3)
+    # --bench: not a fixture but a timing of the reference runtime itself on real-size Llama-3-8B layers (random init on the device,
+    # synthetic tokens): the GPU-side yardstick next to bench.py --layers L (same strategy: ZeRO-2, chunks, no checkpointing)
+    ap.add_argument("--bench", action="store_true")
+    ap.add_argument("--layers", type=int, default=8)
+    ap.add_argument("--seq", type=int, default=8192)
+    ap.add_argument("--gbs", type=int, default=8)
+    ap.add_argument("--chunks", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=2)
     opts = ap.parse_args()
     world_want, over = CASES[opts.case]
     dist.init_process_group("nccl", init_method="env://")
     rank, world = dist.get_rank(), dist.get_world_size()
-    assert world == world_want, "case %s runs on %d ranks" % (opts.case, world_want)
+    assert opts.bench or world == world_want, "case %s runs on %d ranks" % (opts.case, world_want)
     torch.cuda.set_device(rank)
     device = torch.device("cuda", rank)
 
@@ -68,7 +76,10 @@ def main():
     set_seed(1234)
     initialize_model_parallel(tensor_model_parallel_size=1, pipeline_model_parallel_size=1)
     random.model_parallel_cuda_manual_seed(1234)
-    args = RuntimeArgs(model_type="llama", rank=rank, checkpoint_dir={"converted": GOLDEN}, backend="hf")
+    if opts.bench:
+        spec = {"hidden_size": 4096, "intermediate_size": 14336, "num_attention_heads": 32, "num_key_value_heads": 8, "num_hidden_layers": opts.layers,
+                "rms_norm_eps": 1e-5, "vocab_size": 128256, "max_position_embeddings": opts.seq}
+    args = RuntimeArgs(model_type="llama", rank=rank, checkpoint_dir=None if opts.bench else {"converted": GOLDEN}, backend="hf")
     # HEAD's test RuntimeArgs predates context parallelism: every option of the runtime's own parser that it lacks gets the
     # parser's default (galvatron/core/runtime/arguments.py: galvatron_training_args)
     import argparse as _ap
@@ -82,7 +93,7 @@ def main():
     args.model_size = {"dim": spec["hidden_size"], "ffn_dim": spec["intermediate_size"], "n_heads": spec["num_attention_heads"],
                        "n_kv_heads": spec["num_key_value_heads"], "n_layers": spec["num_hidden_layers"], "norm_eps": spec["rms_norm_eps"],
                        "vocab_size": spec["vocab_size"], "n_positions": spec["max_position_embeddings"], "multiple_of": 32}
-    args.global_train_batch_size, args.chunks = 4, 1
+    args.global_train_batch_size, args.chunks = (opts.gbs, opts.chunks) if opts.bench else (4, 1)
     args.mixed_precision, args.use_flash_attn = "bf16", True
     args.default_dp_type, args.pipeline_type = "zero2", "pipedream_flush"
     # reduce_in_fp32 / entropy_in_fp32 stay True, as the reference's own tests run (tests/utils/runtime_args.py:60-62): the loss is
@@ -105,6 +116,41 @@ def main():
     dp_idx, dp = dp_ranks.index(rank), len(dp_ranks)
     gbs, seq = args.global_train_batch_size, spec["max_position_embeddings"]
     g = torch.Generator().manual_seed(11)
+    if opts.bench:
+        batches = [torch.randint(0, spec["vocab_size"], (gbs, seq + 1), generator=g) for _ in range(opts.warmup + opts.steps)]
+        lo, hi = dp_idx * gbs // dp, (dp_idx + 1) * gbs // dp
+
+        def one(x, it):
+            tokens, labels = x[lo:hi, :-1].contiguous().to(device), x[lo:hi, 1:].contiguous().to(device)
+            loss = model.forward_backward([tokens], it, None, loss_func=None, attention_mask=None, labels=labels)
+            optimizer.step()
+            optimizer.zero_grad()
+            return loss
+        for i in range(opts.warmup):
+            one(batches[i], i)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for i in range(opts.warmup, opts.warmup + opts.steps):
+            last = one(batches[i], i)
+        e1.record()
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        rec = {"impl": "reference runtime on GPU (baseline/_ref: FSDP + NCCL + flash-attn 2 + torch ops; torch.optim.Adam on fp32 flat params)",
+               "model": "Llama-3-8B shapes, %d layers" % opts.layers, "seq": seq, "global_bsz": gbs, "chunks": args.chunks, "world": world,
+               "default_dp_type": args.default_dp_type, "steps": opts.steps, "warmup": opts.warmup, "ms_per_step": round(float(ms[0]) / opts.steps, 3),
+               "tokens_per_s": round(gbs * seq * opts.steps / (float(ms[0]) * 1e-3), 1), "last_loss": last,
+               "peak_allocated_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2), "gpu": torch.cuda.get_device_name(0), "torch": torch.__version__}
+        if rank == 0:
+            os.makedirs(opts.out, exist_ok=True)
+            with open(os.path.join(opts.out, "ref_runtime_bench_%dlayers_n%d.json" % (opts.layers, world)), "w") as f:
+                json.dump(rec, f, indent=1)
+            print("REF_BENCH " + json.dumps(rec), flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     losses, grad_norms = [], []
     for it in range(opts.steps):
         x = torch.randint(0, spec["vocab_size"], (gbs, seq + 1), generator=g)

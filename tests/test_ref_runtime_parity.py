@@ -5,8 +5,8 @@ strategy.  This repo's runtime, given the same weights (the same converted check
 optimizer, must reproduce them: the loss of step 0 (pure forward) and of the later steps (which fold in every gradient through
 the optimizer) and, at every step, the norm of all gradient tensors of the job -- CPU host runtime within 1e-4 / 3e-4 / 3e-3
 (observed 7e-6 / 4e-5 / 6e-4: both sides compute in bf16 with fp32 reductions and fp32 cross-entropy, as the reference's own
-tests configure it, tests/utils/runtime_args.py:60-62), GPU product path within 2e-3 / 5e-3 / 1e-2 (the reference's own criterion
-against HF is 5e-3, tests/core/test_tp.py:121).
+tests configure it, tests/utils/runtime_args.py:60-62), GPU product path within 2e-4 / 3e-4 / 3e-3 (observed 1e-5 / 4e-5 / 7e-4;
+north_star asks for 1e-3, the reference's own criterion against HF is 5e-3, tests/core/test_tp.py:121).
 CPU: the host runtime on the oracle backend.  GPU (``-m gpu``): the product path through the C ABI."""
 import glob
 import json
@@ -62,5 +62,5 @@ def test_product_path_matches_reference_runtime(case):
     fx = FIXTURES[case]
     if not torch.cuda.is_available() or torch.cuda.device_count() < fx["world"]:
         pytest.skip("needs %d GPU(s)" % fx["world"])
-    _check(fx, _ours(fx, "cuda"), 2e-3, 5e-3, 1e-2,
+    _check(fx, _ours(fx, "cuda"), 2e-4, 3e-4, 3e-3,        # observed on B200s: 1.0e-5, 4.2e-5, 7.2e-4 (profiles/r02_ref_runtime_parity_gpu.jsonl)
            record=os.path.join(os.path.dirname(HERE), "gpurun_out", "r02_ref_runtime_parity_gpu.jsonl"))
