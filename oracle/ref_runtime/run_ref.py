@@ -101,6 +101,7 @@ def main():
     args.make_vocab_size_divisible_by = 128
     args.untie_embeddings_and_output_weights = True
     args.lr, args.adam_weight_decay = 1e-3, 0.0
+    args.init_method_std = 0.02          # random init on the device (--bench: no checkpoint; tensor_parallel/reset.py:13)
     for k, v in over.items():
         setattr(args, k, v)
     args.vocab_sp = 1 if getattr(args, "use_ulysses", False) else 0
