@@ -231,7 +231,8 @@ def main():
                     print("DEBUG layer", i, "scale", scale["gpt_dec_%d" % (i + 1)], {k: fit(gl[k], wl[k].grad) for k in gl}, flush=True)
             assert abs(mean_loss - float(ref_loss)) <= 5e-3 * abs(float(ref_loss)), report
             assert report["max_grad_err"] < tol, (report, errs)
-            assert report["err_budget_ratio"] <= budget_tol, report
+            if tol != float("inf"):      # (gradient checks off: the fused optimizer consumed the gradients inside the reduce-scatter kernel)
+                assert report["err_budget_ratio"] <= budget_tol, report
             if clip is not None:
                 # clip_grad_norm (core/runtime/utils.py:124-133): the job-wide L2 norm counts every parameter once -- the oracle's
                 # gradients of the un-parallelised model give the expected value -- and every shard is scaled by the same factor
