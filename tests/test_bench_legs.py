@@ -63,7 +63,7 @@ def test_leg_strategies_expand(n):
             assert 0 < arena < 120 << 30, (name, arena)
 
 
-@pytest.mark.parametrize("n", [2] + ([4] if os.environ.get("HGB_SLOW_TESTS") else []))     # a minute per world size on CPU
+@pytest.mark.parametrize("n", [2, 4])
 def test_leg_tiny_strategies_match_the_oracle(n):
     from test_families import launch as launch_family
     bench = _bench()

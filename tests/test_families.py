@@ -9,23 +9,14 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 _PORT = [29300]
 
 
 def launch(world, config, timeout=600, backend="oracle"):
+    from _launch import launch_ranks
     _PORT[0] += 1
-    procs = []
-    for rank in range(world):
-        env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
-                   MASTER_PORT=str(_PORT[0] + os.getpid() % 500), HOST_TEST_CONFIG=json.dumps(config), OMP_NUM_THREADS="1" if world >= 4 else "2",
-                   HOST_TEST_BACKEND=backend)
-        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_family_worker.py")], env=env,
-                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
-    outs = [p.communicate(timeout=timeout)[0] for p in procs]
-    for rank, (p, out) in enumerate(zip(procs, outs)):
-        assert p.returncode == 0, "rank %d failed:\n%s" % (rank, out[-4000:])
-    line = [l for l in outs[0].splitlines() if l.startswith("HOST_TEST_REPORT ")][-1]
-    return json.loads(line[len("HOST_TEST_REPORT "):])
+    return launch_ranks("_family_worker", world, config, _PORT[0] + os.getpid() % 500, timeout=timeout, backend=backend)
 
 
 CASES = {

@@ -10,24 +10,15 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 _PORT = [29600]
 
 
 def launch(world, config, timeout=600, backend="oracle"):
+    from _launch import launch_ranks
     _PORT[0] += 1
-    procs = []
     extra_env = config.pop("_env", {})
-    for rank in range(world):
-        env = dict(os.environ, **extra_env, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
-                   MASTER_PORT=str(_PORT[0] + os.getpid() % 500), HOST_TEST_CONFIG=json.dumps(config), OMP_NUM_THREADS="1" if world >= 4 else "2",
-                   HOST_TEST_BACKEND=backend)
-        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_host_worker.py")], env=env,
-                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
-    outs = [p.communicate(timeout=timeout)[0] for p in procs]
-    for rank, (p, out) in enumerate(zip(procs, outs)):
-        assert p.returncode == 0, "rank %d failed:\n%s" % (rank, out[-4000:])
-    line = [l for l in outs[0].splitlines() if l.startswith("HOST_TEST_REPORT ")][-1]
-    return json.loads(line[len("HOST_TEST_REPORT "):])
+    return launch_ranks("_host_worker", world, config, _PORT[0] + os.getpid() % 500, timeout=timeout, backend=backend, extra_env=extra_env)
 
 
 WORLD1 = {
@@ -181,13 +172,7 @@ def test_world4(name):
     assert rep["max_grad_err"] < 3e-2
 
 
-# the reference's hybrid corpus always; of its six redistributed cases one by default and all with HGB_SLOW_TESTS=1 (15 s each on CPU;
-# the GPU suite, tests/test_gpu_model.py, always runs all of them)
-_WORLD8_DEFAULT = [n for n in sorted(WORLD8) if not n.startswith("ref_redistributed") or n == "ref_redistributed_tp1248_vtp8_sp"
-                   or os.environ.get("HGB_SLOW_TESTS")]
-
-
-@pytest.mark.parametrize("name", _WORLD8_DEFAULT)
+@pytest.mark.parametrize("name", sorted(WORLD8))
 def test_world8(name):
     rep = launch(8, dict(WORLD8[name]), timeout=900)
     assert rep["max_grad_err"] < 3e-2
