@@ -84,3 +84,29 @@ def test_c_mirror_of_group_builder_matches_goldens(bg):
             for kind, key in enumerate(kinds):
                 got = [[rk[(kind * n + i) * 64 + j] for j in range(cnt[kind * n + i])] for i in range(n)]
                 assert got == want[key], (case["name"], rank, key)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline / reference arm may use it.
+    No module of the package (nor the C sources) may name it in an import; the CUDA backend must be what get_backend() builds."""
+    import ast
+    pkg = os.path.join(ROOT, "hetu-galvatron_b200")
+    offenders = []
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            path = os.path.join(dp, f)
+            if f.endswith(".py"):
+                tree = ast.parse(open(path).read())
+                for node in ast.walk(tree):
+                    names = []
+                    if isinstance(node, ast.Import):
+                        names = [a.name for a in node.names]
+                    elif isinstance(node, ast.ImportFrom) and node.module:
+                        names = [node.module]
+                    offenders += [(os.path.relpath(path, ROOT), n) for n in names if n == "oracle" or n.startswith("oracle.")]
+            elif f.endswith((".cu", ".cuh", ".h")):
+                if "oracle/" in open(path, errors="replace").read():
+                    offenders.append((os.path.relpath(path, ROOT), "oracle/ path"))
+    assert not offenders, offenders
+    src = open(os.path.join(pkg, "core", "runtime", "backend.py")).read()
+    assert "class CudaBackend" in src and "OracleBackend" not in src.replace("``oracle/gloo_backend.py``", "")

@@ -22,6 +22,9 @@ def launch(world, config, timeout=600, backend="oracle"):
 CASES = {
     # BASELINE config 1: GPT pure data parallel on one rank (the plumbing case) -- and its BERT twin
     "gpt_world1": (1, dict(_family="gpt")),
+    # ... and at its stated shape: GPT-2 small (12 layers, h 768, 12 heads, vocab 50257, seq 1024), one sample, one rank, on CPU (75 s)
+    "gpt2_small_world1_baseline1": (1, dict(_family="gpt", _spec=dict(n_layer=12, n_embd=768, n_head=12, vocab_size=50257, n_positions=1024),
+                                            global_train_batch_size=1, chunks=1)),
     "bert_world1": (1, dict(_family="bert")),
     "gpt_world1_ckpt_chunks2": (1, dict(_family="gpt", global_checkpoint=1, chunks=2)),
     "gpt_tp2": (2, dict(_family="gpt", global_tp_deg=2, vocab_tp=2)),
