@@ -585,7 +585,7 @@ class CudaBackend:
     def layernorm_bwd(self, dy, x, weight, mean, rstd):
         x2, dy2 = x.reshape(-1, x.shape[-1]), dy.reshape(-1, x.shape[-1])
         dx = torch.empty_like(x2)
-        npart = min(444, max(1, x2.shape[0]))       # 3 CTAs of 256 threads x 76 registers per SM
+        npart = min(444, max(1, x2.shape[0]))       # partial-sum rows (one per CTA; summed below)
         dwp = torch.empty(npart, x2.shape[1], dtype=torch.float32, device=x.device)
         dbp = torch.empty_like(dwp)
         self.bg.check(self.bg.lib().bg_layernorm_bwd(_p(dy2), _p(x2), _p(weight), _p(mean), _p(rstd), _p(dx), _p(dwp), _p(dbp),
