@@ -3,3 +3,4 @@ from .BertModel_hybrid_parallel import bert_model_hp, construct_hybrid_parallel_
 from .BertModel_sequential import BertModelInfo, construct_sequential_model
 from .BertModel_tensor_parallel import BertLayer_tp, construct_tensor_parallel_model
 from .meta_configs import config_from_meta, set_model_config
+from .BertModel_checkpoint import load_bert_module  # noqa: E402,F401

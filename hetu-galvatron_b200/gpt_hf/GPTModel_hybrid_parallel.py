@@ -2,6 +2,7 @@
 from ..core.runtime.hybrid_parallel_config import get_hybrid_parallel_configs_api
 from ..core.runtime.hybrid_parallel_model import construct_hybrid_parallel_model_api
 from ..llama_hf.LlamaModel_hybrid_parallel import estimate_arena_bytes
+from .GPTModel_checkpoint import load_gpt_module
 from .GPTModel_sequential import (GPTCls_, GPTEmbeddings_, GPTModelInfo, GPTPreNorm_, construct_sequential_model)
 from .GPTModel_tensor_parallel import GPTLayer_tp, GPTSkeleton, construct_tensor_parallel_model
 from .meta_configs import config_from_meta, set_model_config
@@ -20,7 +21,7 @@ def construct_hybrid_parallel_model(model, model_config, training_args, hybrid_p
         model, model_config, training_args, hybrid_parallel_configs, GPTModelInfo, construct_sequential_model,
         construct_tensor_parallel_model, wrap_block_name=[GPTLayer_tp], wrap_checkpoint_block_name=[GPTLayer_tp],
         wrap_other_block_name=[GPTEmbeddings_, GPTPreNorm_, GPTCls_], tied_wte_attr_names=None, layernorm_name=["LayerNorm", "ln_f"],
-        all_block_name=[GPTEmbeddings_, GPTLayer_tp, GPTPreNorm_, GPTCls_], load_module_func=None)
+        all_block_name=[GPTEmbeddings_, GPTLayer_tp, GPTPreNorm_, GPTCls_], load_module_func=load_gpt_module)
 
 
 def get_gpt_config(args, overwrite_args=True):

@@ -137,3 +137,38 @@ def split_qkv(p, cfg):
     w = p["qkv"].view(n, 3, hn, -1)
     b = p["qkv_b"].view(n, 3, hn)
     return [w[:, i].reshape(n * hn, -1) for i in range(3)], [b[:, i].reshape(n * hn) for i in range(3)]
+
+
+def to_hf_state_dict(w, cfg, family):
+    """Megatron-layout oracle weights -> the HF ``GPT2LMHeadModel`` / ``BertForMaskedLM`` state dict they correspond to (the mapping
+    tests/test_oracle_gpt_bert.py pins; inverse of what the families' checkpoint loaders do).  GPT-2's ``Conv1D`` weights are [in, out]."""
+    sd = {}
+    if family == "gpt":
+        sd.update({"transformer.wte.weight": w["wte"], "transformer.wpe.weight": w["wpe"], "transformer.ln_f.weight": w["norm"],
+                   "transformer.ln_f.bias": w["norm_b"], "lm_head.weight": w["lm_head"]})
+        for i, p in enumerate(w["layers"]):
+            (q, k, v), (qb, kb, vb) = split_qkv(p, cfg)
+            pre = "transformer.h.%d." % i
+            sd.update({pre + "ln_1.weight": p["ln1"], pre + "ln_1.bias": p["ln1_b"], pre + "ln_2.weight": p["ln2"], pre + "ln_2.bias": p["ln2_b"],
+                       pre + "attn.c_attn.weight": torch.cat([q, k, v]).t(), pre + "attn.c_attn.bias": torch.cat([qb, kb, vb]),
+                       pre + "attn.c_proj.weight": p["dense"].t(), pre + "attn.c_proj.bias": p["dense_b"],
+                       pre + "mlp.c_fc.weight": p["h_to_4h"].t(), pre + "mlp.c_fc.bias": p["h_to_4h_b"],
+                       pre + "mlp.c_proj.weight": p["4h_to_h"].t(), pre + "mlp.c_proj.bias": p["4h_to_h_b"]})
+        return sd
+    sd.update({"bert.embeddings.word_embeddings.weight": w["word"], "bert.embeddings.position_embeddings.weight": w["pos"],
+               "bert.embeddings.token_type_embeddings.weight": w["type"], "bert.embeddings.LayerNorm.weight": w["emb_ln"],
+               "bert.embeddings.LayerNorm.bias": w["emb_ln_b"], "cls.predictions.transform.dense.weight": w["transform"],
+               "cls.predictions.transform.dense.bias": w["transform_b"], "cls.predictions.transform.LayerNorm.weight": w["transform_ln"],
+               "cls.predictions.transform.LayerNorm.bias": w["transform_ln_b"], "cls.predictions.decoder.weight": w["decoder"],
+               "cls.predictions.decoder.bias": w["decoder_b"], "cls.predictions.bias": w["decoder_b"]})
+    for i, p in enumerate(w["layers"]):
+        (q, k, v), (qb, kb, vb) = split_qkv(p, cfg)
+        pre = "bert.encoder.layer.%d." % i
+        sd.update({pre + "attention.self.query.weight": q, pre + "attention.self.query.bias": qb, pre + "attention.self.key.weight": k,
+                   pre + "attention.self.key.bias": kb, pre + "attention.self.value.weight": v, pre + "attention.self.value.bias": vb,
+                   pre + "attention.output.dense.weight": p["dense"], pre + "attention.output.dense.bias": p["dense_b"],
+                   pre + "attention.output.LayerNorm.weight": p["ln1"], pre + "attention.output.LayerNorm.bias": p["ln1_b"],
+                   pre + "intermediate.dense.weight": p["h_to_4h"], pre + "intermediate.dense.bias": p["h_to_4h_b"],
+                   pre + "output.dense.weight": p["4h_to_h"], pre + "output.dense.bias": p["4h_to_h_b"],
+                   pre + "output.LayerNorm.weight": p["ln2"], pre + "output.LayerNorm.bias": p["ln2_b"]})
+    return sd

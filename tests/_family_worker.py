@@ -78,6 +78,7 @@ def main():
     family = over.pop("_family")
     spec = dict(TINY[family], **over.pop("_spec", {}))
     tol = over.pop("_tol", 3e-2)
+    golden_ckpt = over.pop("_golden_ckpt", None)
     use_cuda = os.environ.get("HOST_TEST_BACKEND", "oracle") == "cuda"
     from oracle import gpt_bert_ref as ref
     import smoke_model as sm
@@ -105,6 +106,33 @@ def main():
     model = build(config, args)
     opt, _ = get_optimizer_and_param_scheduler(model, args)
     w = assemble(model, family, world, rank, lambda u: u.read_full_params())
+    report0 = {}
+    if golden_ckpt:   # the weights the model loaded must be HF's, bit for bit, whatever the tensor-parallel degree
+        cfg0 = dict(n_heads=config.num_attention_heads, head_dim=config.hidden_size // config.num_attention_heads)
+        hf = ref.to_hf_state_dict(w, cfg0, family)
+        want = {}
+        for fname in sorted(os.listdir(golden_ckpt)):
+            if not fname.endswith(".pt"):
+                continue
+            blob = torch.load(os.path.join(golden_ckpt, fname), map_location="cpu", weights_only=True)
+            stem = fname[:-3]
+            for k, v in blob.items():
+                if stem == "transformer_embedding":
+                    want["lm_head.weight" if k == "weight" else "transformer." + k] = v
+                elif stem == "transformer_ln_f":
+                    want["transformer.ln_f." + k] = v
+                elif stem.startswith("transformer_h_"):
+                    want["transformer.h.%s.%s" % (stem.rsplit("_", 1)[1], k)] = v
+                elif stem == "bert_embeddings":
+                    want["bert.embeddings." + k] = v
+                elif stem.startswith("bert_encoder_layer_"):
+                    want["bert.encoder.layer.%s.%s" % (stem.rsplit("_", 1)[1], k)] = v
+                elif stem == "cls_predictions":
+                    want["cls.predictions." + k] = v
+        assert set(want) == set(hf), sorted(set(want) ^ set(hf))
+        bad = [k for k in want if not torch.equal(want[k].float(), hf[k].float())]
+        assert not bad, "loaded weights differ from the HF checkpoint: %s" % bad
+        report0["ckpt_tensors_bit_exact"] = len(want)
     cfg = dict(hidden=config.hidden_size, ffn=config.intermediate_size, n_heads=config.num_attention_heads,
                head_dim=config.hidden_size // config.num_attention_heads, n_layers=config.num_hidden_layers, vocab=args.padded_vocab_size,
                seq=config.max_position_embeddings, eps=args.norm_epsilon, gelu_tanh=True)
@@ -167,7 +195,7 @@ def main():
     lt = torch.tensor([loss if loss is not None else 0.0, 1.0 if loss is not None else 0.0], dtype=torch.float64, device=dev)
     dist.all_reduce(lt)
     mean_loss = float(lt[0] / lt[1])
-    report = {"loss": mean_loss, "ref_loss": float(ref_loss), "max_grad_err": max(errs.values()), "worst": max(errs, key=errs.get)}
+    report = dict(report0, loss=mean_loss, ref_loss=float(ref_loss), max_grad_err=max(errs.values()), worst=max(errs, key=errs.get))
     if use_cuda:
         report["launches"] = be.launch_count()
         report["fused_calls"] = dict(getattr(be, "n_fused", {}))
