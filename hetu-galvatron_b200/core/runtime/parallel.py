@@ -207,6 +207,10 @@ class ShardedUnit:
         self._reduced_this_step = False
         self._pending = False          # backward ran since the last reduction
         self.n_unshard = self.n_reduce = 0
+        # tied word embeddings (C14, pipeline/grad_reduce.py:98-131): {"param": the tied weight, "deferred": bool}.  Such a unit does not
+        # reduce at its own post-backward: PipelineParallel.finish_step first exchanges the unsharded gradient with the partner unit
+        # (the other copy of the matrix), then launches the reduction.
+        self._tie = None
 
     @property
     def master_grad(self):
@@ -372,6 +376,13 @@ class ShardedUnit:
             if self.g_pool is not None:
                 raise RuntimeError("pooled zero3 gradients need a reduction after every backward (chunks == 1 or --no_async_grad_reduce)")
             return
+        if self._tie is not None:           # reduced once per step, by finish_step, after the exchange with the other copy
+            self._tie["deferred"] = True
+            return
+        self.reduce_now()
+
+    def reduce_now(self):
+        """Launch this unit's gradient reduction over its sharded-data-parallel group (C2/C3) on what G holds now."""
         if not self._pending:
             self.release_grads()
             return
@@ -395,6 +406,22 @@ class ShardedUnit:
         # --no_async_grad_reduce) must not overwrite G before it has been read -- _pre_backward waits for this event
         self._reduce_event = be.reduce_done_event()
         self.release_grads()
+
+    def write_master(self, full):
+        """Replace the fp32 master by (this rank's part of) ``full`` -- a flat fp32 tensor of ``padded`` elements, identical on every
+        member of the group -- and refresh the gathered low-precision copy."""
+        with torch.no_grad():
+            if self.dp_type == "ddp" or self.group.size == 1:
+                self.flat_param.data.copy_(full)
+            else:
+                self.flat_param.data.copy_(full[self.rank_in_group * self.shard_elems:(self.rank_in_group + 1) * self.shard_elems])
+            self._w_version += 1
+            if self.w_pool is None:
+                self.w_flat.copy_(full.to(self.param_dtype))
+            else:
+                if self._w_valid:
+                    self.reshard()
+                self._w_valid = False
 
     def finish_step(self):
         """Make the optimizer (current stream) wait for this step's reductions."""

@@ -164,9 +164,7 @@ class PipelineParallel(nn.Module):
         self.sequence_parallel, self.shape_order = args.sequence_parallel, args.shape_order
         self.async_grad_reduce = args.async_grad_reduce
         self.embedding_group, self.tied_wte_attr_names = embedding_group, tied_wte_attr_names
-        if tied_wte_attr_names is not None:
-            raise NotImplementedError("tied input/output embeddings (C14): the Llama family leaves them untied "
-                                      "(LlamaModel_hybrid_parallel.py:44)")
+        self._tied_units = []           # filled by _setup_tied_embeddings once the stage's units exist
         self.units = []
         self._links = {}
         self.real_chunks = self.chunks
@@ -200,12 +198,86 @@ class PipelineParallel(nn.Module):
                                pool_slots=int(getattr(args, "zero3_pool_slots", 0)), pool_grads=pool_grads,
                                load_module_func=load_module_func, all_block_name=all_block_name, load=getattr(args, "load", None),
                                distributed_checkpoint=bool(getattr(args, "distributed_checkpoint", False)),
-                               reserve_save_buffer=bool(getattr(args, "save", None)))
+                               reserve_save_buffer=bool(getattr(args, "save", None)) or self.tied_wte_attr_names is not None)
             self.units.append(unit)
             wrapped.append(DataParallelModule(module, unit, checkpoint=False))
         for a, b in zip(wrapped[:-1], wrapped[1:]):
             a.next_unit, b.prev_unit = b.unit, a.unit
         self.model_cur_stage = PipeSequential(*wrapped)
+        if self.tied_wte_attr_names is not None:
+            self._setup_tied_embeddings()
+
+    # ---- tied word embeddings (C14) ------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _tied_param(unit, attr):
+        """The word-embedding matrix inside a unit: the 2-D parameter under attribute ``attr`` of the wrapped block ("" = the block
+        itself: the output head), as ``tied_wte_attr_names`` names it (hybrid_parallel_model.py:176, GPTModel_hybrid_parallel.py:42)."""
+        cands = [(n, p) for n, p in unit.module.named_parameters() if p.dim() == 2 and (not attr or attr in n.split("."))]
+        if not cands:
+            raise ValueError("tied_wte_attr_names: no 2-D parameter under %r in unit %s" % (attr, unit.name))
+        return max(cands, key=lambda np_: np_[1].numel())
+
+    def _setup_tied_embeddings(self):
+        """``sync_embedding`` (pipeline.py:228-242): the input embedding (first unit of the first stage) and the output head (last unit
+        of the last stage) hold two copies of ONE matrix.  At construction both become the average of the two initialisations --
+        what the reference's all-reduce(AVG) over the embedding group does; after every backward their unsharded gradients are summed
+        into both (``finalize_wte_grads_func`` :1031-1050 -- the reference's pp > 1 rule, applied here for pp = 1 too, where the
+        reference averages sequentially and lets the copies drift apart), so identical optimizer steps keep them identical."""
+        be = get_backend()
+        first, last = self.is_pipeline_first_stage(), self.is_pipeline_last_stage()
+        embed = self.units[0] if first else None
+        head = self.units[-1] if last else None
+        mine = [(u, attr) for u, attr in ((embed, self.tied_wte_attr_names[0]), (head, self.tied_wte_attr_names[-1])) if u is not None]
+        if not mine:
+            return
+        if self.group_size > 1 and not getattr(be, "supports_tied_embedding_exchange", False):
+            raise NotImplementedError("tied embeddings across pipeline stages need an all-reduce over the embedding group (first + last "
+                                      "stage): not wired into this backend; run with untie_embeddings_and_output_weights=True or pp_deg=1")
+        fulls = []
+        for u, attr in mine:
+            if u.g_pool is not None:
+                raise ValueError("tied embeddings cannot use pooled zero3 gradient buffers (set --embed_sdp 0 or --zero3_pool_slots 0)")
+            name, p = self._tied_param(u, attr)
+            u._tie = {"param": p, "name": name, "deferred": False}
+            full = be.gather_master(u).clone()
+            fulls.append((u, full, u.named_slices(full)[name]))
+            self._tied_units.append(u)
+        if self.group_size == 1:
+            (_, _, a), (_, _, b) = fulls
+            if a.shape != b.shape:
+                raise ValueError("tied embeddings need the same vocabulary sharding on both rows: %s vs %s" % (tuple(a.shape), tuple(b.shape)))
+            avg = (a + b) / 2
+            a.copy_(avg)
+            b.copy_(avg)
+        else:
+            (_, _, a), = fulls
+            a.copy_(be.all_reduce(a.contiguous(), self.embedding_group) / 2)
+        for u, full, _ in fulls:
+            u.write_master(full)
+
+    def _finalize_tied(self):
+        """``finalize_wte_grads_func``: both copies of the tied matrix receive the SUM of their unsharded gradients; then the deferred
+        reductions of the tied units are launched."""
+        if not self._tied_units:
+            return
+        be = get_backend()
+        for u in self._tied_units:
+            p = u._tie["param"]
+            if u._tie["deferred"] and not u.grad_started(p):
+                p._bg_grad.zero_()
+                u.mark_grad(p)
+        live = [u for u in self._tied_units if u._tie["deferred"]]
+        if live:
+            if self.group_size == 1:
+                a, b = (u._tie["param"]._bg_grad for u in self._tied_units)
+                a.add_(b)
+                b.copy_(a)
+            else:
+                g = self._tied_units[0]._tie["param"]._bg_grad
+                g.copy_(be.all_reduce(g.contiguous(), self.embedding_group))
+        for u in live:
+            u.reduce_now()
+            u._tie["deferred"] = False
 
     def gen_sp_layernorm_info(self, *a, **k):
         """The reference attaches LayerNorm offsets to each FSDP state here (pipeline.py:244-256); the ShardedUnit finds its
@@ -248,6 +320,7 @@ class PipelineParallel(nn.Module):
             u.begin_step()
 
     def finish_step(self):
+        self._finalize_tied()
         if self.units:
             self.units[0].finish_step()
 

@@ -13,14 +13,12 @@ def get_hybrid_parallel_configs(model_config, training_args):
 
 
 def construct_hybrid_parallel_model(model, model_config, training_args, hybrid_parallel_configs):
-    if not getattr(training_args, "untie_embeddings_and_output_weights", True):
-        # GPTModel_hybrid_parallel.py:42 ties wte and lm_head by default (gradient exchange C14, grad_reduce.py:98-131): not built here
-        raise NotImplementedError("tied input/output embeddings are not implemented: run the GPT family with "
-                                  "untie_embeddings_and_output_weights=True (the default of this runtime)")
+    # GPTModel_hybrid_parallel.py:42: wte and lm_head are tied unless --untie_embeddings_and_output_weights (this runtime's default: untied)
+    tied = None if getattr(training_args, "untie_embeddings_and_output_weights", True) else ["wte", ""]
     return construct_hybrid_parallel_model_api(
         model, model_config, training_args, hybrid_parallel_configs, GPTModelInfo, construct_sequential_model,
         construct_tensor_parallel_model, wrap_block_name=[GPTLayer_tp], wrap_checkpoint_block_name=[GPTLayer_tp],
-        wrap_other_block_name=[GPTEmbeddings_, GPTPreNorm_, GPTCls_], tied_wte_attr_names=None, layernorm_name=["LayerNorm", "ln_f"],
+        wrap_other_block_name=[GPTEmbeddings_, GPTPreNorm_, GPTCls_], tied_wte_attr_names=tied, layernorm_name=["LayerNorm", "ln_f"],
         all_block_name=[GPTEmbeddings_, GPTLayer_tp, GPTPreNorm_, GPTCls_], load_module_func=load_gpt_module)
 
 

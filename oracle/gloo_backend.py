@@ -103,6 +103,8 @@ class OracleBackend:
     def reserve_checkpoint_gather(self, group, nbytes):
         pass
 
+    supports_tied_embedding_exchange = True     # all_reduce works over any rank list (the embedding group: first + last stage)
+
     def gather_master(self, unit):
         if unit.dp_type == "ddp" or unit.group.size == 1:
             return unit.flat_param.data

@@ -107,6 +107,11 @@ def main():
     opt, _ = get_optimizer_and_param_scheduler(model, args)
     w = assemble(model, family, world, rank, lambda u: u.read_full_params())
     report0 = {}
+    tied = family == "gpt" and not getattr(args, "untie_embeddings_and_output_weights", True)
+    if tied:        # one matrix, two copies: they must be identical, and the oracle then uses ONE leaf for both (HF's tie_word_embeddings)
+        assert torch.equal(w["wte"], w["lm_head"]), "tied embeddings: wte and lm_head differ after construction"
+        w["lm_head"] = w["wte"]
+        report0["tied"] = True
     if golden_ckpt:   # the weights the model loaded must be HF's, bit for bit, whatever the tensor-parallel degree
         cfg0 = dict(n_heads=config.num_attention_heads, head_dim=config.hidden_size // config.num_attention_heads)
         hf = ref.to_hf_state_dict(w, cfg0, family)
@@ -219,10 +224,13 @@ def main():
     for i, wl in enumerate(w["layers"]):
         for t in wl.values():
             leaf_scale[id(t)] = scale[layer_units[i]]
-    leaves = [t for t in leaves_of(w) if t.grad is not None]
+    leaves = list({id(t): t for t in leaves_of(w) if t.grad is not None}.values())      # (tied embeddings: one leaf, listed twice)
     with torch.no_grad():
         for t in leaves:
             t.grad.mul_(leaf_scale[id(t)])
+    if tied:        # ... and after the step the two copies of the product must still be one matrix
+        w_after = assemble(model, family, world, rank, lambda u: u.read_full_params())
+        assert torch.equal(w_after["wte"], w_after["lm_head"]), "tied embeddings drifted apart after one optimizer step"
     ref_opt = torch.optim.AdamW(leaves, lr=args.lr, weight_decay=args.adam_weight_decay,
                                 betas=(getattr(args, "adam_beta1", 0.9), getattr(args, "adam_beta2", 0.999)), eps=getattr(args, "adam_eps", 1e-8))
     ref_opt.step()

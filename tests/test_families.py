@@ -28,6 +28,16 @@ CASES = {
     "bert_world1": (1, dict(_family="bert")),
     "gpt_world1_ckpt_chunks2": (1, dict(_family="gpt", global_checkpoint=1, chunks=2)),
     "gpt_tp2": (2, dict(_family="gpt", global_tp_deg=2, vocab_tp=2)),
+    # tied input / output embeddings (the reference's default for GPT, GPTModel_hybrid_parallel.py:42; C14): one rank, ZeRO-2 and ZeRO-3
+    # shards, vocabulary-parallel, two microbatches, and across two pipeline stages (all-reduce over the embedding group)
+    "gpt_tied_world1": (1, dict(_family="gpt", untie_embeddings_and_output_weights=False)),
+    "gpt_tied_world1_chunks2_ckpt": (1, dict(_family="gpt", untie_embeddings_and_output_weights=False, chunks=2, global_checkpoint=1)),
+    "gpt_tied_dp2_zero2": (2, dict(_family="gpt", untie_embeddings_and_output_weights=False, default_dp_type="zero2", chunks=2)),
+    "gpt_tied_dp2_zero3": (2, dict(_family="gpt", untie_embeddings_and_output_weights=False, sdp=1, embed_sdp=1, zero3_pool_slots=0)),
+    "gpt_tied_tp2_megatron_sp": (2, dict(_family="gpt", untie_embeddings_and_output_weights=False, global_tp_deg=2, vocab_tp=2, sequence_parallel=True)),
+    "gpt_tied_pp2_1f1b": (2, dict(_family="gpt", untie_embeddings_and_output_weights=False, pp_deg=2, chunks=2, pipeline_type="pipedream_flush")),
+    "gpt_tied_pp2_gpipe_tp2": (4, dict(_family="gpt", untie_embeddings_and_output_weights=False, pp_deg=2, chunks=2, pipeline_type="gpipe",
+                                       global_tp_deg=2, vocab_tp=2)),
     "gpt_tp2_megatron_sp": (2, dict(_family="gpt", global_tp_deg=2, vocab_tp=2, sequence_parallel=True)),
     "gpt_dp2_zero3": (2, dict(_family="gpt", sdp=1, embed_sdp=1)),
     "bert_tp2": (2, dict(_family="bert", global_tp_deg=2, vocab_tp=2)),

@@ -121,3 +121,28 @@ def test_out_of_vocabulary_label_follows_megatron():
     got = ref._token_loss(logits, labels, torch.float64)
     assert torch.allclose(got[0, 1], torch.logsumexp(logits[0, 1], -1) - logits[0, 1].max())
     assert torch.allclose(got[1, 0], torch.logsumexp(logits[1, 0], -1) - logits[1, 0, 3])
+
+
+def test_gpt_oracle_with_tied_embeddings_matches_hf():
+    """HF GPT-2's default: lm_head IS wte.  The oracle expresses it as one leaf used twice (what tests/_family_worker.py does for the
+    tied runs of the product): its gradient must be HF's gradient of the shared matrix (embedding part + head part)."""
+    transformers = pytest.importorskip("transformers")
+    w = _randomize(ref.init_weights(CFG, "gpt", seed=5, std=0.05, dtype=torch.float64), 2)
+    w["lm_head"] = w["wte"]
+    conf = transformers.GPT2Config(n_embd=CFG["hidden"], n_layer=CFG["n_layers"], n_head=CFG["n_heads"], vocab_size=CFG["vocab"],
+                                   n_positions=CFG["seq"], n_inner=CFG["ffn"], layer_norm_epsilon=CFG["eps"], resid_pdrop=0.0, embd_pdrop=0.0,
+                                   attn_pdrop=0.0, activation_function="gelu_new", tie_word_embeddings=True, attn_implementation="eager")
+    hf = transformers.GPT2LMHeadModel(conf).double()
+    sd = {k: v.detach() for k, v in ref.to_hf_state_dict(w, CFG, "gpt").items()}
+    missing, unexpected = hf.load_state_dict(sd, strict=False)
+    assert not [k for k in missing if "attn.bias" not in k and "masked_bias" not in k] and not unexpected, (missing, unexpected)
+    assert hf.lm_head.weight is hf.transformer.wte.weight
+    tokens = torch.randint(0, CFG["vocab"], (3, 24))
+    labels = torch.randint(0, CFG["vocab"], (3, 24))
+    _, loss = ref.gpt_forward_loss(w, tokens, labels, CFG, dtype=torch.float64)
+    loss.backward()
+    logits = hf(input_ids=tokens).logits
+    hf_loss = torch.nn.functional.cross_entropy(logits.reshape(-1, CFG["vocab"]), labels.reshape(-1))
+    torch.testing.assert_close(loss.detach(), hf_loss.detach(), rtol=2e-6, atol=2e-6)
+    hf_loss.backward()
+    torch.testing.assert_close(w["wte"].grad, hf.transformer.wte.weight.grad, rtol=1e-5, atol=1e-8)
